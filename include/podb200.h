@@ -1,0 +1,225 @@
+/*
+ * podb200.h -- C ABI of the B200-native probabilistic-inference path.
+ *
+ * Drop-in boundary for the hot path of asharakeh/pod_compare (reference paths relative to
+ * /root/reference/src).  The reference has no native layer: this path is pure Python over
+ * torch / torchvision / detectron2, so each entry point below names the reference *Python*
+ * code whose arithmetic it replaces; INTEGRATION.md shows the ctypes binding a maintainer
+ * adds in probabilistic_inference.py to call them.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 for a bad argument, >0 for a CUDA error code;
+ *     pod_last_error() returns the thread-local message.  No exceptions cross the ABI.
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the caller owns every
+ *     buffer (torch-allocated); the library allocates nothing that outlives a call.
+ *   - `stream` is a cudaStream_t passed as void*; no call synchronises the device.
+ *   - activations are channels-last: map n, pixel (y*W+x), channel c  ->  ((n*H+y)*W+x)*C+c.
+ *   - "split" tensors are the fp16 pair (hi, lo) with  x*scale ~= hi + lo  (hi = rn_fp16(x*scale),
+ *     lo = rn_fp16(x*scale - hi)); three fp16 tensor-core products hi*hi' + hi*lo' + lo*hi'
+ *     accumulated in fp32 reproduce the fp32 convolution to ~2^-22 relative.
+ */
+#ifndef PODB200_H_
+#define PODB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POD_ABI_VERSION 1
+
+const char* pod_last_error(void);
+int pod_version(void);
+/* 1 if the current device can run the sm_100a kernels (compute capability 10.x). */
+int pod_device_ok(void);
+
+/* ---- counter-based random streams (parity contract with oracle/philox.py) -------------------
+ * Replace torch's generator at the three places the reference draws randomness:
+ * nn.Dropout (probabilistic_modeling/probabilistic_retinanet.py:422-424), Normal.rsample
+ * (probabilistic_inference/probabilistic_inference.py:291-294) and MultivariateNormal.rsample
+ * (:351-356).  These three fill functions expose the streams for tests. */
+int pod_philox_dropout_mask(uint8_t* keep_hwc, int H, int W, int C, uint64_t seed, int image, int sample,
+                            int pass, int tower, int layer, int level, double p, void* stream);
+int pod_philox_logit_normals(float* out_draws_n_k, int draws, int n_anchor, int K, uint64_t seed, int image,
+                             int level, void* stream);
+int pod_philox_box_normals(float* out_draws_m_4, const int64_t* anchor_ids, int M, int draws, uint64_t seed,
+                           int image, void* stream);
+
+/* ---- operand preparation ---------------------------------------------------------------------
+ * FPN feature maps (NCHW fp32, as the backbone returns them at probabilistic_retinanet.py:99-100)
+ * -> channels-last fp16 split pair. */
+int pod_nchw_to_nhwc_split(const float* src_nchw, int NB, int C, int H, int W, float scale,
+                           void* dst_hi, void* dst_lo, void* stream);
+/* Same layout change, fp32 out (input of the SIMT cross-check convolution). */
+int pod_nchw_to_nhwc_f32(const float* src_nchw, int NB, int C, int H, int W, float* dst, void* stream);
+/* nn.Conv2d weight (Cout, Cin, 3, 3) fp32 -> K-major GEMM operand rows [Cout_pad][9*Cin] with
+ * k = (ky*3+kx)*Cin + ci, as fp16 split pair scaled by `scale` (rows >= Cout are zero).
+ * Replaces nothing arithmetic: it is the weight-pack step of the checkpoint loader
+ * (probabilistic_inference.py:72-84). */
+int pod_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int Cout_pad, float scale,
+                         void* dst_hi, void* dst_lo, void* stream);
+/* Same K-major order, fp32, transposed to [9*Cin][Cout_pad] for the SIMT convolution. */
+int pod_pack_conv_weight_f32(const float* w_oihw, int Cout, int Cin, int Cout_pad, float* dst, void* stream);
+
+/* Dropout description for one convolution launch: map index n of the OUTPUT decodes as
+ * image = image0 + n / (samples*passes), sample = (n / passes) % samples, pass = pass0 + n % passes.
+ * p == 0 disables dropout. */
+typedef struct pod_dropout {
+  double p;
+  uint64_t seed;
+  int image0;
+  int samples;
+  int passes;
+  int pass0;
+  int tower;
+  int layer;
+  int level;
+} pod_dropout;
+
+/* MC-dropout replication of the (mask-independent) first tower layer, SURVEY Q2:
+ * x (NB_in, H*W, C) fp32 post-ReLU  ->  NB_in*samples*passes masked, rescaled, split copies.
+ * Replaces the first nn.Dropout of every tower evaluation (probabilistic_retinanet.py:422-424,518-523). */
+int pod_mask_expand_split(const float* x, int NB_in, int HW, int C, const pod_dropout* d, float scale,
+                          void* dst_hi, void* dst_lo, void* stream);
+
+/* ---- the head convolutions (probabilistic_retinanet.py:401-441,458-484,517-523) -------------
+ * 3x3 / stride 1 / pad 1 convolution over NB channels-last maps as an implicit GEMM on the
+ * tcgen05 tensor cores (TMA-fed, fp32 accumulation in TMEM, fp16x3 split operands).
+ *   in_hi/in_lo : (NB, H, W, Cin) fp16 split pair scaled by in_scale; consecutive maps are
+ *                 in_map_stride ELEMENTS apart (lets a launch read every 2nd map).
+ *   w_hi/w_lo   : [Cout_pad][9*Cin] from pod_pack_conv_weight, scaled by w_scale
+ *   bias        : Cout_pad fp32
+ * mode POD_OUT_HIDDEN : y = dropout(relu(conv + bias)) -> split pair (NB,H,W,Cout_pad) scaled by out_scale
+ * mode POD_OUT_RAW    : y = conv + bias (relu if `relu`) -> fp32, element (n, pixel, c<Cout) at
+ *                       out_f32[n*out_map_stride + pixel*out_pixel_stride + c]; with Cout = A*K this
+ *                       IS permute_to_N_HWA_K (probabilistic_retinanet.py:343-349). */
+enum { POD_OUT_HIDDEN = 0, POD_OUT_RAW = 1 };
+typedef struct pod_conv_args {
+  const void* in_hi;
+  const void* in_lo;
+  int64_t in_map_stride;
+  float in_scale;
+  int NB, H, W, Cin;
+  const void* w_hi;
+  const void* w_lo;
+  float w_scale;
+  const float* bias;
+  int Cout, Cout_pad;
+  int mode;
+  int relu;
+  void* out_hi;
+  void* out_lo;
+  float out_scale;
+  float* out_f32;
+  int64_t out_map_stride;
+  int64_t out_pixel_stride;
+  pod_dropout drop;
+} pod_conv_args;
+int pod_conv3x3_tc(const pod_conv_args* a, void* stream);
+/* Channels per pipeline stage of the tcgen05 kernel: 32 (SWIZZLE_64B operand tiles, deeper pipeline,
+ * default) or 64 (SWIZZLE_128B).  Process-wide tuning knob; results are identical. */
+int pod_conv3x3_tc_set_kblock(int bk);
+/* Device-side error word of the last tcgen05 launch on this thread (0 = ok; set when a bounded
+ * barrier wait expired).  Host pointer out. */
+int pod_conv3x3_tc_status(int* status_host);
+
+/* Plain fp32 SIMT convolution with the same semantics (cross-check of the tensor-core kernel;
+ * not on the product path). in (NB,H,W,Cin) fp32, w from pod_pack_conv_weight_f32. */
+int pod_conv3x3_simt(const float* in, int NB, int H, int W, int Cin, const float* w_kc, const float* bias,
+                     int Cout, int Cout_pad, int relu, const pod_dropout* drop, float* out,
+                     int64_t out_map_stride, int64_t out_pixel_stride, void* stream);
+
+/* ---- per-anchor sample statistics (probabilistic_inference.py:214-270, quirk Q1) -------------
+ * x (B, S, n) fp32 -> out (B, n):  ((x0 + x0) + x1 + ... + x_{S-2}) / S  in that fp32 order
+ * (S == 1: copy). */
+int pod_sample_mean_q1(const float* x, int B, int S, int64_t n, float* out, void* stream);
+
+/* ---- scores and per-level top-k (probabilistic_inference.py:283-308) ------------------------
+ * For image b, level l (anchors [off_l, off_l+n_l) of R): class probabilities
+ *   with logvar : mean_j sigmoid(mu + eps_j * sqrt(exp(logvar))), j < draws (STREAM_LOGIT)
+ *   without     : sigmoid(mu)
+ * then max/argmax over K.  probs (B,R,K), score (B,R), cls (B,R) int32. */
+int pod_scores(const float* logits, const float* logvar /*nullable*/, int B, int R, int K, int n_levels,
+               const int* level_off /*host, n_levels+1*/, int draws, uint64_t seed, int image0,
+               float* probs, float* score, int* cls, void* stream);
+/* Per (image, level): the min(topk, n_l) highest scores, descending, ties -> lower anchor index,
+ * then those > thresh.  cand_idx (B, cap) holds GLOBAL anchor ids, level l's segment starts at
+ * seg_off[l] (host array, n_levels+1, seg_off[l+1]-seg_off[l] = min(topk, n_l)); cand_cnt (B, n_levels). */
+int pod_topk_levels(const float* score, int B, int R, int n_levels, const int* level_off_host,
+                    const int* seg_off_host, int topk, float thresh, int* cand_idx, int* cand_cnt, void* stream);
+
+/* ---- decode + covariance of the candidates (probabilistic_inference.py:310-388,
+ *      inference_utils.py:337-371,510-547, modeling_utils.py:4-22) ----------------------------
+ * One warp per candidate.  Outputs are written at the COMPACTED position
+ * m = sum_{l'<l} cnt[l'] + rank (the order of the reference's torch.cat over levels).
+ *   mean_delta (B,R,4); mean_regvar (B,R,cd) or NULL; sample_delta (B,S,R,4) or NULL (S>1: epistemic)
+ *   anchors (R,4); probs/score/cls from pod_scores
+ * out: boxes (B,cap,4) cov (B,cap,16) scores (B,cap) classes (B,cap) i32 probs (B,cap,K) count (B)
+ *      cand_anchor (B,cap) global anchor id per compacted candidate; has_cov = cov is meaningful. */
+typedef struct pod_decode_args {
+  const float* mean_delta;
+  const float* mean_regvar;
+  int cov_dims;
+  const float* sample_delta;
+  int S;
+  const float* anchors;
+  const float* probs;
+  const float* score;
+  const int* cls;
+  const int* cand_idx;
+  const int* cand_cnt;
+  int B, R, K, n_levels, cap;
+  const int* seg_off_host;
+  int box_draws;
+  uint64_t seed;
+  int image0;
+  float wx, wy, ww, wh;
+  float* out_boxes;
+  float* out_cov;
+  float* out_scores;
+  int* out_classes;
+  float* out_probs;
+  int* out_count;
+  int* out_anchor;
+} pod_decode_args;
+int pod_decode_cov(const pod_decode_args* a, void* stream);
+
+/* ---- NMS / BayesOD fusion / rescale (inference_utils.py:12-54,292-334,374-425;
+ *      probabilistic_inference.py:536-636; torchvision ops/boxes.py:51-120 + cpu/nms_kernel.cpp) ---
+ * One CTA per image.  mode: 0 standard NMS, 1 BayesOD.  nms_variant: 0 per-class ("vanilla"),
+ * 1 coordinate-offset trick, 2 auto = torchvision's CPU rule (4*M > 4000 -> vanilla).
+ * box_merge: 0 bayesian_inference, 1 covariance_intersection; cls_merge: 0 max_score,
+ * 1 bayesian_inference (mean of member vectors).
+ * in : candidates from pod_decode_cov (B,cap,...) + count (B); has_cov: 0 -> zero covariances
+ * out: det_* (B,max_dets,...) + det_count (B) after scale/clip/nonempty; keep (B,max_dets) = NMS
+ *      survivor indices into the candidate list BEFORE the nonempty filter, keep_count (B). */
+typedef struct pod_nms_args {
+  const float* boxes;
+  const float* cov;
+  const float* scores;
+  const int* classes;
+  const float* probs;
+  const int* count;
+  int B, cap, K;
+  int has_cov;
+  int mode, nms_variant, box_merge, cls_merge;
+  double nms_thresh;
+  double affinity;
+  int max_dets;
+  int in_h, in_w, out_h, out_w;
+  float* det_boxes;
+  float* det_cov;
+  float* det_scores;
+  int* det_classes;
+  float* det_probs;
+  int* det_count;
+  int* keep;
+  int* keep_count;
+} pod_nms_args;
+int pod_nms_fuse(const pod_nms_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PODB200_H_ */

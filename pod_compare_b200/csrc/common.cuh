@@ -1,0 +1,119 @@
+// Shared device/host helpers of libpodb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/podb200.h"
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: thread-local message, int return codes (no exceptions cross the ABI)
+// ---------------------------------------------------------------------------------------------
+void pod_set_error(const char* fmt, ...);
+
+#define POD_REQUIRE(cond, ...)                                   \
+  do {                                                           \
+    if (!(cond)) {                                               \
+      pod_set_error(__VA_ARGS__);                                \
+      return -1;                                                 \
+    }                                                            \
+  } while (0)
+
+#define POD_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      pod_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return (int)_e;                                                                           \
+    }                                                                                           \
+  } while (0)
+
+#define POD_LAUNCH_CHECK()                                                                      \
+  do {                                                                                          \
+    cudaError_t _e = cudaGetLastError();                                                        \
+    if (_e != cudaSuccess) {                                                                    \
+      pod_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return (int)_e;                                                                           \
+    }                                                                                           \
+  } while (0)
+
+static inline int pod_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 and the three streams (contract: oracle/philox.py)
+// ---------------------------------------------------------------------------------------------
+#define POD_STREAM_DROPOUT 0x0D120F01u
+#define POD_STREAM_LOGIT 0x0D120F02u
+#define POD_STREAM_BOX 0x0D120F03u
+
+struct PhiloxKey {
+  uint32_t k0, k1;
+};
+
+__host__ __device__ inline PhiloxKey pod_key(uint64_t seed, uint32_t stream) {
+  PhiloxKey k;
+  k.k0 = (uint32_t)(seed & 0xFFFFFFFFull);
+  k.k1 = (uint32_t)(seed >> 32) ^ stream;
+  return k;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, PhiloxKey key) {
+  uint32_t k0 = key.k0, k1 = key.k1;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0;
+    const uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+__host__ __device__ inline uint32_t pod_dropout_threshold(double p) {
+  // floor(p * 2^32) for 0 <= p < 1, evaluated in double like the oracle
+  double t = p * 4294967296.0;
+  if (t <= 0.0) return 0u;
+  if (t >= 4294967295.0) return 4294967295u;
+  return (uint32_t)t;
+}
+
+__host__ __device__ inline uint32_t pod_dropout_c1(int level, int layer, int tower, int pass) {
+  return (uint32_t)(level & 0xFF) | ((uint32_t)(layer & 0xFF) << 8) | ((uint32_t)(tower & 0xFF) << 16) |
+         ((uint32_t)(pass & 0xFF) << 24);
+}
+
+// uniform in (0,1) from the top 23 bits; exact in fp32
+__device__ __forceinline__ float pod_u23(uint32_t w) { return ((float)(w >> 9) + 0.5f) * 1.1920928955078125e-07f; }
+
+// Box-Muller pair: r = sqrt(-2 ln ua); (r cos 2pi ub, r sin 2pi ub)
+__device__ __forceinline__ void pod_box_muller(uint32_t wa, uint32_t wb, float& n0, float& n1) {
+  const float ua = pod_u23(wa), ub = pod_u23(wb);
+  const float r = sqrtf(-2.0f * logf(ua));
+  float s, c;
+  sincospif(2.0f * ub, &s, &c);
+  n0 = r * c;
+  n1 = r * s;
+}
+
+// fp16 split of x*scale: hi = rn(x*scale), lo = rn(x*scale - hi)
+__device__ __forceinline__ void pod_split_h(float xs, __half& hi, __half& lo) {
+  hi = __float2half_rn(xs);
+  lo = __float2half_rn(xs - __half2float(hi));
+}
+
+// 1/(1-p) as torch computes the dropout scale: fp32(1) / fp32(1-p)
+__host__ __device__ inline float pod_dropout_scale(double p) { return 1.0f / (float)(1.0 - p); }

@@ -1,0 +1,506 @@
+// 3x3 head convolution as an implicit GEMM on the Blackwell tensor cores (sm_100a).
+//
+//   D[pixel, cout] = sum_{tap, cin} X[pixel + tap, cin] * Wt[cout, tap*Cin + cin]
+//
+// * A operand: channels-last activation tiles (8 rows x 16 cols of pixels = 128 GEMM rows, BK
+//   channels) fetched by TMA from a 4-D tensor map (C, W, H, maps); the 3x3 taps are nine shifted
+//   boxes and the zero padding is TMA's out-of-bounds fill.
+// * B operand: packed weight rows [Cout_pad][9*Cin] fetched by TMA (2-D map).
+// * fp32 fidelity on fp16 tensor cores: both operands arrive as (hi, lo) fp16 pairs and every
+//   K-step issues three tcgen05.mma (hi*hi', hi*lo', lo*hi') into one fp32 TMEM accumulator.
+// * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
+//   warps 4-7 = epilogue (tcgen05.ld -> bias/ReLU/Philox dropout -> fp16 split or fp32 store).
+//   Two TMEM accumulators (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+// * persistent: grid = min(#tiles, #SMs), static round-robin over (map, tile_y, tile_x).
+//
+// Replaces nn.Conv2d(+ReLU+Dropout) of the reference head,
+// /root/reference/src/probabilistic_modeling/probabilistic_retinanet.py:401-441,458-484,517-523.
+#include "common.cuh"
+#include <cuda.h>
+#include <cstring>
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int TILE_H = 8;
+constexpr int TILE_W = 16;
+constexpr int UMMA_K = 16;
+constexpr int ACC_COLS = 256;           // TMEM columns reserved per accumulator buffer
+constexpr int NUM_THREADS = 256;
+constexpr long long WAIT_LIMIT_CYCLES = 4000000000LL;   // ~2 s: bounded waits, never hang the box
+
+__device__ int g_status = 0;            // 0 ok; else code of the barrier wait that expired
+
+struct Params {
+  CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
+  int NB, H, W, Cin;
+  int tiles_x, tiles_y, num_tiles;
+  int Cout, Cout_pad;
+  int relu;
+  float acc_scale;      // 1 / (in_scale * w_scale)
+  float out_scale;
+  const float* bias;
+  __half* out_hi;
+  __half* out_lo;
+  float* out_f32;
+  long long out_map_stride, out_pixel_stride;
+  pod_dropout drop;
+  uint32_t drop_thr;
+  float drop_scale;
+  PhiloxKey key;
+};
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: returns false (and records `code`) if the barrier did not flip within ~2 s
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int code) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > WAIT_LIMIT_CYCLES) {
+      atomicCAS(&g_status, 0, code);
+      return false;
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tm) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): rows of ROW_BYTES
+// (= one swizzle span), 8-row atoms SBO apart, Blackwell descriptor version 1.
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  static_assert(ROW_BYTES == 128 || ROW_BYTES == 64, "swizzle span");
+  constexpr uint64_t SBO = (uint64_t)(8 * ROW_BYTES) >> 4;
+  constexpr uint64_t LAYOUT = ROW_BYTES == 128 ? 2 : 4;   // SWIZZLE_128B : SWIZZLE_64B
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (SBO << 32) | (1ull << 46) | (LAYOUT << 61);
+}
+
+template <int BN, int BK>
+struct Cfg {
+  static constexpr int ROW_BYTES = BK * 2;
+  static constexpr int A_BYTES = BM * ROW_BYTES;
+  static constexpr int B_BYTES = BN * ROW_BYTES;
+  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+  static_assert(STAGES >= 2, "pipeline too shallow");
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
+  static_assert(A_BYTES % 1024 == 0 && B_BYTES % 512 == 0, "operand alignment");
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major both, N>>3, M>>4
+  static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+
+template <int BN, int BK, int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_constant__ Params P) {
+  using C = Cfg<BN, BK>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  uint8_t* smem = smem_dyn + (smem_base - smem_u32(smem_dyn));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.tm_a_hi);
+    tma_prefetch_desc(&P.tm_a_lo);
+    tma_prefetch_desc(&P.tm_b_hi);
+    tma_prefetch_desc(&P.tm_b_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_s, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int kb_per_tap = P.Cin / BK;
+  const int kb_total = 9 * kb_per_tap;
+  const int tiles_per_map = P.tiles_x * P.tiles_y;
+
+  if (warp == 0 && lane == 0) {
+    // ================================ TMA producer ================================
+    uint32_t stage = 0, phase = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
+      const int n = tile / tiles_per_map, r = tile % tiles_per_map;
+      const int y0 = (r / P.tiles_x) * TILE_H, x0 = (r % P.tiles_x) * TILE_W;
+      for (int tap = 0; tap < 9 && ok; ++tap) {
+        const int yy = y0 + tap / 3 - 1, xx = x0 + tap % 3 - 1;
+        for (int cb = 0; cb < kb_per_tap; ++cb) {
+          if (!mbar_wait(&empty_bar[stage], phase ^ 1u, 1)) { ok = false; break; }
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)C::STAGE_BYTES);
+          uint8_t* s = smem + (size_t)stage * C::STAGE_BYTES;
+          tma_load_4d(&P.tm_a_hi, &full_bar[stage], s, cb * BK, xx, yy, n);
+          tma_load_4d(&P.tm_a_lo, &full_bar[stage], s + C::A_BYTES, cb * BK, xx, yy, n);
+          tma_load_2d(&P.tm_b_hi, &full_bar[stage], s + 2 * C::A_BYTES, tap * P.Cin + cb * BK, 0);
+          tma_load_2d(&P.tm_b_lo, &full_bar[stage], s + 2 * C::A_BYTES + C::B_BYTES, tap * P.Cin + cb * BK, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ================================ MMA issuer ==================================
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
+      if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 2)) break;
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+      for (int kb = 0; kb < kb_total; ++kb) {
+        if (!mbar_wait(&full_bar[stage], phase, 3)) { ok = false; break; }
+        tcgen05_fence_after();
+        const uint32_t sa_hi = smem_base + stage * C::STAGE_BYTES;
+        const uint32_t sa_lo = sa_hi + C::A_BYTES;
+        const uint32_t sb_hi = sa_hi + 2 * C::A_BYTES;
+        const uint32_t sb_lo = sb_hi + C::B_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint32_t koff = k * UMMA_K * 2;
+          const uint64_t ah = make_smem_desc<C::ROW_BYTES>(sa_hi + koff);
+          const uint64_t al = make_smem_desc<C::ROW_BYTES>(sa_lo + koff);
+          const uint64_t bh = make_smem_desc<C::ROW_BYTES>(sb_hi + koff);
+          const uint64_t bl = make_smem_desc<C::ROW_BYTES>(sb_lo + koff);
+          umma_f16(d_tmem, al, bh, C::IDESC, (kb | k) != 0 ? 1u : 0u);   // small terms first
+          umma_f16(d_tmem, ah, bl, C::IDESC, 1u);
+          umma_f16(d_tmem, ah, bh, C::IDESC, 1u);
+        }
+        umma_commit(&empty_bar[stage]);                    // frees the smem slot when the MMAs retire
+        if (kb == kb_total - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      acc ^= 1u;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ====================================
+    const int ew = warp - 4;                 // == warp % 4: the TMEM lane quadrant this warp may read
+    const int m = ew * 32 + lane;            // GEMM row == TMEM lane == pixel of the tile
+    const int reps = P.drop.samples * P.drop.passes;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      const int n = tile / tiles_per_map, r = tile % tiles_per_map;
+      const int py = (r / P.tiles_x) * TILE_H + m / TILE_W, px = (r % P.tiles_x) * TILE_W + m % TILE_W;
+      const bool valid = py < P.H && px < P.W;
+      const int pixel = py * P.W + px;
+      if (!mbar_wait(&tfull_bar[acc], acc_phase, 4)) break;
+      tcgen05_fence_after();
+      uint32_t c1 = 0, sample = 0, image = 0;
+      if (MODE == POD_OUT_HIDDEN && P.drop_thr != 0u) {
+        image = (uint32_t)(P.drop.image0 + n / reps);
+        sample = (uint32_t)((n / P.drop.passes) % P.drop.samples);
+        c1 = pod_dropout_c1(P.drop.level, P.drop.layer, P.drop.tower, P.drop.pass0 + n % P.drop.passes);
+      }
+      const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * ACC_COLS;
+#pragma unroll 1
+      for (int ch = 0; ch < BN; ch += 16) {
+        uint32_t raw[16];
+        __syncwarp();                          // tcgen05.ld is warp-collective (.sync.aligned)
+        tmem_ld16(trow + ch, raw);
+        tmem_ld_wait();
+        if (ch + 16 >= BN) {
+          // all TMEM reads of this thread are done: hand the accumulator back to the MMA warp
+          tcgen05_fence_before();
+          mbar_arrive(&tempty_bar[acc]);
+        }
+        if (valid) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          v[i] = fmaf(__uint_as_float(raw[i]), P.acc_scale, __ldg(P.bias + ch + i));
+          if (P.relu) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (MODE == POD_OUT_HIDDEN) {
+          if (P.drop_thr != 0u) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t q = (uint32_t)(((long long)pixel * P.Cout_pad + ch + g * 4) >> 2);
+              const uint4 w = philox4x32_10(q, c1, sample, image, P.key);
+              v[g * 4 + 0] = w.x >= P.drop_thr ? v[g * 4 + 0] * P.drop_scale : 0.f;
+              v[g * 4 + 1] = w.y >= P.drop_thr ? v[g * 4 + 1] * P.drop_scale : 0.f;
+              v[g * 4 + 2] = w.z >= P.drop_thr ? v[g * 4 + 2] * P.drop_scale : 0.f;
+              v[g * 4 + 3] = w.w >= P.drop_thr ? v[g * 4 + 3] * P.drop_scale : 0.f;
+            }
+          }
+          uint32_t ph[8], pl[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            __half h0, l0, h1, l1;
+            pod_split_h(v[2 * i] * P.out_scale, h0, l0);
+            pod_split_h(v[2 * i + 1] * P.out_scale, h1, l1);
+            ph[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            pl[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+          }
+          const long long o = ((long long)n * P.H * P.W + pixel) * P.Cout_pad + ch;
+          uint4* dh = reinterpret_cast<uint4*>(P.out_hi + o);
+          uint4* dl = reinterpret_cast<uint4*>(P.out_lo + o);
+          dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+          dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+          dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+        } else {
+          float* o = P.out_f32 + (long long)n * P.out_map_stride + (long long)pixel * P.out_pixel_stride + ch;
+          if (ch + 16 <= P.Cout && ((P.out_map_stride | P.out_pixel_stride) & 3) == 0) {
+            float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) o4[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (ch + i < P.Cout) o[i] = v[i];
+          }
+        }
+        }  // valid
+      }
+      acc ^= 1u;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled)p;
+  }
+  return fn;
+}
+
+static int encode_act(CUtensorMap* tm, const void* base, int Cin, int W, int H, int NB, long long map_stride_elems, int BK) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  POD_REQUIRE(enc, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+  cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)map_stride_elems * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BK, TILE_W, TILE_H, 1};
+  cuuint32_t est[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, est,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  POD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: CUresult %d", (int)r);
+  return 0;
+}
+
+static int encode_wt(CUtensorMap* tm, const void* base, int Ktot, int rows, int BK, int BN) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  POD_REQUIRE(enc, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+  cuuint32_t est[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, est,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  POD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed: CUresult %d", (int)r);
+  return 0;
+}
+
+template <int BN, int BK, int MODE>
+static int launch(const Params& P, cudaStream_t st) {
+  using C = Cfg<BN, BK>;
+  auto kern = k_conv3x3_tc<BN, BK, MODE>;
+  static bool configured = false;
+  if (!configured) {
+    POD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  const int grid = P.num_tiles < pod_num_sms() ? P.num_tiles : pod_num_sms();
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(P);
+  POD_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BK, int MODE>
+static int dispatch_bn(const Params& P, cudaStream_t st) {
+  switch (P.Cout_pad) {
+    case 256: return launch<256, BK, MODE>(P, st);
+    case 128: return launch<128, BK, MODE>(P, st);
+    case 96: return launch<96, BK, MODE>(P, st);
+    case 80: return launch<80, BK, MODE>(P, st);
+    case 64: return launch<64, BK, MODE>(P, st);
+    case 48: return launch<48, BK, MODE>(P, st);
+    default: break;
+  }
+  pod_set_error("pod_conv3x3_tc: unsupported Cout_pad %d (supported: 48,64,80,96,128,256)", P.Cout_pad);
+  return -1;
+}
+
+}  // namespace tc
+
+static int g_tc_bk = 32;   // K-block (channels per pipeline stage): 32 -> SWIZZLE_64B, 64 -> SWIZZLE_128B
+
+extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_kblock(int bk) {
+  POD_REQUIRE(bk == 32 || bk == 64, "pod_conv3x3_tc_set_kblock: 32 or 64");
+  g_tc_bk = bk;
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_conv_args* a, void* stream) {
+  using namespace tc;
+  POD_REQUIRE(a, "pod_conv3x3_tc: null args");
+  POD_REQUIRE(a->in_hi && a->in_lo && a->w_hi && a->w_lo && a->bias, "pod_conv3x3_tc: null operand");
+  POD_REQUIRE(a->NB > 0 && a->H > 0 && a->W > 0 && a->Cin >= 64 && a->Cin % 64 == 0, "pod_conv3x3_tc: bad shape (Cin%%64)");
+  POD_REQUIRE(a->Cout > 0 && a->Cout <= a->Cout_pad, "pod_conv3x3_tc: Cout > Cout_pad");
+  POD_REQUIRE(a->in_map_stride >= (int64_t)a->H * a->W * a->Cin && a->in_map_stride % 8 == 0,
+              "pod_conv3x3_tc: in_map_stride too small or not 16-byte aligned");
+  POD_REQUIRE(((uintptr_t)a->in_hi | (uintptr_t)a->in_lo | (uintptr_t)a->w_hi | (uintptr_t)a->w_lo) % 16 == 0,
+              "pod_conv3x3_tc: operands must be 16-byte aligned");
+  POD_REQUIRE(a->in_scale > 0.f && a->w_scale > 0.f, "pod_conv3x3_tc: scales must be positive");
+  Params P;
+  memset(&P, 0, sizeof(P));
+  const int BK = g_tc_bk;
+  int rc;
+  if ((rc = encode_act(&P.tm_a_hi, a->in_hi, a->Cin, a->W, a->H, a->NB, a->in_map_stride, BK))) return rc;
+  if ((rc = encode_act(&P.tm_a_lo, a->in_lo, a->Cin, a->W, a->H, a->NB, a->in_map_stride, BK))) return rc;
+  if ((rc = encode_wt(&P.tm_b_hi, a->w_hi, 9 * a->Cin, a->Cout_pad, BK, a->Cout_pad))) return rc;
+  if ((rc = encode_wt(&P.tm_b_lo, a->w_lo, 9 * a->Cin, a->Cout_pad, BK, a->Cout_pad))) return rc;
+  P.NB = a->NB; P.H = a->H; P.W = a->W; P.Cin = a->Cin;
+  P.tiles_x = (a->W + TILE_W - 1) / TILE_W;
+  P.tiles_y = (a->H + TILE_H - 1) / TILE_H;
+  const long long nt = (long long)P.tiles_x * P.tiles_y * a->NB;
+  POD_REQUIRE(nt < (1ll << 31), "pod_conv3x3_tc: too many tiles");
+  P.num_tiles = (int)nt;
+  P.Cout = a->Cout; P.Cout_pad = a->Cout_pad;
+  P.relu = a->relu;
+  P.acc_scale = 1.0f / (a->in_scale * a->w_scale);
+  P.out_scale = a->out_scale;
+  P.bias = a->bias;
+  P.out_hi = (__half*)a->out_hi; P.out_lo = (__half*)a->out_lo; P.out_f32 = a->out_f32;
+  P.out_map_stride = a->out_map_stride; P.out_pixel_stride = a->out_pixel_stride;
+  P.drop = a->drop;
+  if (P.drop.samples <= 0) P.drop.samples = 1;
+  if (P.drop.passes <= 0) P.drop.passes = 1;
+  P.drop_thr = 0;
+  P.drop_scale = 1.f;
+  if (a->mode == POD_OUT_HIDDEN) {
+    POD_REQUIRE(a->out_hi && a->out_lo && a->out_scale > 0.f, "pod_conv3x3_tc: hidden mode needs out_hi/out_lo/out_scale");
+    POD_REQUIRE(a->Cout == a->Cout_pad, "pod_conv3x3_tc: hidden mode needs Cout == Cout_pad");
+    POD_REQUIRE(((uintptr_t)a->out_hi | (uintptr_t)a->out_lo) % 16 == 0, "pod_conv3x3_tc: outputs must be 16-byte aligned");
+    if (a->drop.p > 0.0) {
+      POD_REQUIRE(a->drop.p < 1.0, "pod_conv3x3_tc: dropout p must be < 1");
+      P.drop_thr = pod_dropout_threshold(a->drop.p);
+      P.drop_scale = pod_dropout_scale(a->drop.p);
+      P.key = pod_key(a->drop.seed, POD_STREAM_DROPOUT);
+    }
+  } else if (a->mode == POD_OUT_RAW) {
+    POD_REQUIRE(a->out_f32 && a->out_pixel_stride >= a->Cout, "pod_conv3x3_tc: raw mode needs out_f32 / pixel stride");
+  } else {
+    POD_REQUIRE(false, "pod_conv3x3_tc: unknown mode %d", a->mode);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BK == 64) {
+    return a->mode == POD_OUT_HIDDEN ? dispatch_bn<64, POD_OUT_HIDDEN>(P, st) : dispatch_bn<64, POD_OUT_RAW>(P, st);
+  }
+  return a->mode == POD_OUT_HIDDEN ? dispatch_bn<32, POD_OUT_HIDDEN>(P, st) : dispatch_bn<32, POD_OUT_RAW>(P, st);
+}
+
+extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_status(int* status_host) {
+  POD_REQUIRE(status_host, "pod_conv3x3_tc_status: null");
+  int v = 0;
+  POD_CUDA(cudaMemcpyFromSymbol(&v, tc::g_status, sizeof(int)));
+  *status_host = v;
+  if (v != 0) {
+    int zero = 0;
+    POD_CUDA(cudaMemcpyToSymbol(tc::g_status, &zero, sizeof(int)));
+  }
+  return 0;
+}

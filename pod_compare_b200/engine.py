@@ -1,0 +1,279 @@
+"""Host-side orchestration of the B200 probabilistic-inference path (features -> detections).
+
+Mirrors, for a BATCH of images, what the reference does for one image in
+`RetinaNetProbabilisticPredictor` (reference src/probabilistic_inference/probabilistic_inference.py):
+    head forward over N MC-dropout samples / E ensemble members   (:199-209, probabilistic_retinanet.py:104-108,517-523)
+    Q1 sample means                                               (:214-270)
+    scores, per-level top-k, threshold                            (:283-308)
+    decode + aleatoric / epistemic covariance                     (:310-388)
+    standard NMS or BayesOD fusion + rescale                      (:390-407, :536-636, inference_utils.py:374-425)
+All arithmetic runs in libpodb200 (hand-written sm_100a CUDA); this file only sequences launches
+and owns the (torch-allocated) device buffers.
+
+Scheduling facts used: the first tower layer (conv+ReLU) does not depend on the dropout
+mask, so it is evaluated once per image and tower and replicated into the N x passes masked copies;
+in eval mode the second tower evaluation of the reference is bit-identical to the first and is
+shared.  Samples and passes are folded into the GEMM M dimension (maps), so one launch per
+(level, tower, layer) covers every image, sample and pass of the chunk.
+"""
+import math
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import ops
+from ._cabi import POD_OUT_HIDDEN, POD_OUT_RAW, PodError
+
+ACT_SCALE = 16.0          # fp16 split scale of activations: |x| < 4094, abs. resolution 2^-28
+TOWER_CLS, TOWER_BOX = 0, 1
+
+
+def _pad_cout(c):
+    for p in (48, 64, 80, 96, 128, 256):
+        if c <= p:
+            return p
+    raise PodError("unsupported output channel count %d" % c)
+
+
+@dataclass
+class PackedConv:
+    w_hi: torch.Tensor
+    w_lo: torch.Tensor
+    bias: torch.Tensor
+    w_scale: float
+    cout: int
+    cout_pad: int
+
+
+def pack_conv(weight, bias, device):
+    w = weight.detach().to(device=device, dtype=torch.float32).contiguous()
+    cout = w.shape[0]
+    cout_pad = _pad_cout(cout)
+    scale = ops.pow2_scale(float(w.abs().max()), 1024.0)
+    hi, lo = ops.pack_conv_weight(w, cout_pad, scale)
+    b = torch.zeros((cout_pad,), dtype=torch.float32, device=device)
+    b[:cout] = bias.detach().to(device=device, dtype=torch.float32)
+    return PackedConv(hi, lo, b, scale, cout, cout_pad)
+
+
+class HeadWeights:
+    """One weight set of the reference head (state-dict keys as in
+    reference src/probabilistic_modeling/probabilistic_retinanet.py:401-484) packed for the
+    tensor-core kernel."""
+
+    def __init__(self, state_dict, use_dropout, cls_var, bbox_cov, num_convs=4, device="cuda"):
+        step = 3 if use_dropout else 2
+        sd = state_dict
+        self.towers = [[], []]
+        for i in range(num_convs):
+            self.towers[TOWER_CLS].append(pack_conv(sd["head.cls_subnet.%d.weight" % (i * step)],
+                                                    sd["head.cls_subnet.%d.bias" % (i * step)], device))
+            self.towers[TOWER_BOX].append(pack_conv(sd["head.bbox_subnet.%d.weight" % (i * step)],
+                                                    sd["head.bbox_subnet.%d.bias" % (i * step)], device))
+        self.cls_score = pack_conv(sd["head.cls_score.weight"], sd["head.cls_score.bias"], device)
+        self.bbox_pred = pack_conv(sd["head.bbox_pred.weight"], sd["head.bbox_pred.bias"], device)
+        self.cls_var = pack_conv(sd["head.cls_var.weight"], sd["head.cls_var.bias"], device) if cls_var else None
+        self.bbox_cov = pack_conv(sd["head.bbox_cov.weight"], sd["head.bbox_cov.bias"], device) if bbox_cov else None
+
+
+@dataclass
+class PathConfig:
+    """The values the predictor reads from cfg / the model object."""
+    num_classes: int = 7
+    num_anchors: int = 9
+    dropout_rate: float = 0.0
+    cls_var: bool = False
+    bbox_cov: bool = False
+    cov_dims: int = 4
+    cls_var_num_samples: int = 10
+    box_num_samples: int = 1000
+    topk: int = 1000
+    score_thresh: float = 0.05
+    nms_thresh: float = 0.5
+    max_dets: int = 100
+    reg_weights: tuple = (1.0, 1.0, 1.0, 1.0)
+    affinity: float = 0.9
+    box_merge: str = "bayesian_inference"
+    cls_merge: str = "max_score"
+
+
+class HeadEngine:
+    """Runs the head + statistics + post-processing for a chunk of images on one GPU."""
+
+    def __init__(self, pc: PathConfig, weight_sets: List[HeadWeights], device="cuda"):
+        self.pc = pc
+        self.ws = weight_sets
+        self.device = torch.device(device)
+        self._buf = {}
+
+    # ------------------------------------------------------------------ buffers (reused across calls)
+    def _get(self, name, numel, dtype):
+        t = self._buf.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = torch.empty((numel,), dtype=dtype, device=self.device)
+            self._buf[name] = t
+        return t
+
+    # ------------------------------------------------------------------ head
+    def _conv_hidden(self, src, NB, H, W, pcv, dst, drop):
+        ops.conv3x3_tc(src[0], src[1], ACT_SCALE, NB, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, pcv.cout,
+                       pcv.cout_pad, POD_OUT_HIDDEN, True, out_hi=dst[0], out_lo=dst[1], out_scale=ACT_SCALE, drop=drop)
+
+    def _conv_out(self, src, NB, H, W, pcv, out, out_offset, out_map_stride, in_map_stride=None, in_offset=0):
+        ops.conv3x3_tc(src[0], src[1], ACT_SCALE, NB, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, pcv.cout,
+                       pcv.cout_pad, POD_OUT_RAW, False, out_f32=out, out_offset=out_offset,
+                       out_map_stride=out_map_stride, out_pixel_stride=pcv.cout,
+                       in_map_stride=in_map_stride, in_offset=in_offset)
+
+    def head_mc(self, feats, n_mc, seed, image0):
+        """MC-dropout head loop: feats = list over levels of (B,256,H,W) fp32.
+        Returns raw per-sample outputs, each (B, N, R, D)."""
+        pc, w = self.pc, self.ws[0]
+        B = feats[0].shape[0]
+        A, K = pc.num_anchors, pc.num_classes
+        level_hw = [tuple(f.shape[-2:]) for f in feats]
+        level_off = [0]
+        for (h, wd) in level_hw:
+            level_off.append(level_off[-1] + h * wd * A)
+        R = level_off[-1]
+        passes = 2 if (pc.cls_var or pc.bbox_cov) else 1
+        dev = self.device
+        raw = {"logits": torch.empty((B, n_mc, R, K), dtype=torch.float32, device=dev),
+               "deltas": torch.empty((B, n_mc, R, 4), dtype=torch.float32, device=dev),
+               "logvar": torch.empty((B, n_mc, R, K), dtype=torch.float32, device=dev) if pc.cls_var else None,
+               "regvar": torch.empty((B, n_mc, R, pc.cov_dims), dtype=torch.float32, device=dev) if pc.bbox_cov else None}
+        max_hw = max(h * wd for h, wd in level_hw)
+        nmaps = B * n_mc * passes
+        act = [(self._get("a%d_hi" % i, nmaps * max_hw * 256, torch.float16),
+                self._get("a%d_lo" % i, nmaps * max_hw * 256, torch.float16)) for i in range(2)]
+        c1 = self._get("c1", B * max_hw * 256, torch.float32)
+        for lvl, f in enumerate(feats):
+            H, W = level_hw[lvl]
+            HW = H * W
+            fhi, flo = ops.nchw_to_nhwc_split(f.contiguous(), ACT_SCALE)
+            for tower in (TOWER_CLS, TOWER_BOX):
+                tw = w.towers[tower]
+                has_var = pc.cls_var if tower == TOWER_CLS else pc.bbox_cov
+                t_passes = 2 if has_var else 1
+                # layer 0: conv + ReLU once per image, then N x passes masked copies (Q2 hoist)
+                p0 = tw[0]
+                ops.conv3x3_tc(fhi, flo, ACT_SCALE, B, H, W, 256, p0.w_hi, p0.w_lo, p0.w_scale, p0.bias, 256, 256,
+                               POD_OUT_RAW, True, out_f32=c1, out_map_stride=HW * 256, out_pixel_stride=256)
+                d0 = ops.make_dropout(pc.dropout_rate, seed, image0, n_mc, t_passes, 0, tower, 0, lvl)
+                ops.mask_expand_split(c1[: B * HW * 256].view(B, HW, 256), d0, ACT_SCALE, act[0][0], act[0][1])
+                cur = 0
+                NB = B * n_mc * t_passes
+                for layer in range(1, len(tw)):
+                    d = ops.make_dropout(pc.dropout_rate, seed, image0, n_mc, t_passes, 0, tower, layer, lvl)
+                    self._conv_hidden(act[cur], NB, H, W, tw[layer], act[cur ^ 1], d)
+                    cur ^= 1
+                # output convs: pass-0 maps feed the mean head, pass-1 maps the variance head (Q2)
+                mean_pc, var_pc = (w.cls_score, w.cls_var) if tower == TOWER_CLS else (w.bbox_pred, w.bbox_cov)
+                mean_out = raw["logits"] if tower == TOWER_CLS else raw["deltas"]
+                D = mean_pc.cout // A
+                self._conv_out(act[cur], B * n_mc, H, W, mean_pc, mean_out, level_off[lvl] * D, R * D,
+                               in_map_stride=t_passes * HW * 256, in_offset=0)
+                if has_var:
+                    var_out = raw["logvar"] if tower == TOWER_CLS else raw["regvar"]
+                    Dv = var_pc.cout // A
+                    self._conv_out(act[cur], B * n_mc, H, W, var_pc, var_out, level_off[lvl] * Dv, R * Dv,
+                                   in_map_stride=2 * HW * 256, in_offset=HW * 256)
+        return raw, level_off
+
+    def head_eval(self, feats, members=None):
+        """Deterministic head (eval mode): one forward per weight set; the reference's second tower
+        evaluation is identical to the first and is shared.  Returns (B, E, R, D) raw outputs."""
+        pc = self.pc
+        members = members if members is not None else list(range(len(self.ws)))
+        E = len(members)
+        B = feats[0].shape[0]
+        A, K = pc.num_anchors, pc.num_classes
+        level_hw = [tuple(f.shape[-2:]) for f in feats]
+        level_off = [0]
+        for (h, wd) in level_hw:
+            level_off.append(level_off[-1] + h * wd * A)
+        R = level_off[-1]
+        dev = self.device
+        raw = {"logits": torch.empty((B, E, R, K), dtype=torch.float32, device=dev),
+               "deltas": torch.empty((B, E, R, 4), dtype=torch.float32, device=dev),
+               "logvar": torch.empty((B, E, R, K), dtype=torch.float32, device=dev) if pc.cls_var else None,
+               "regvar": torch.empty((B, E, R, pc.cov_dims), dtype=torch.float32, device=dev) if pc.bbox_cov else None}
+        max_hw = max(h * wd for h, wd in level_hw)
+        act = [(self._get("a%d_hi" % i, B * max_hw * 256, torch.float16),
+                self._get("a%d_lo" % i, B * max_hw * 256, torch.float16)) for i in range(2)]
+        for lvl, f in enumerate(feats):
+            H, W = level_hw[lvl]
+            fhi, flo = ops.nchw_to_nhwc_split(f.contiguous(), ACT_SCALE)
+            for e, mi in enumerate(members):
+                w = self.ws[mi]
+                for tower in (TOWER_CLS, TOWER_BOX):
+                    tw = w.towers[tower]
+                    src, cur = (fhi, flo), 0
+                    for layer in range(len(tw)):
+                        self._conv_hidden(src, B, H, W, tw[layer], act[cur], None)
+                        src = act[cur]
+                        cur ^= 1
+                    mean_pc, var_pc = (w.cls_score, w.cls_var) if tower == TOWER_CLS else (w.bbox_pred, w.bbox_cov)
+                    mean_out = raw["logits"] if tower == TOWER_CLS else raw["deltas"]
+                    D = mean_pc.cout // A
+                    self._conv_out(src, B, H, W, mean_pc, mean_out, (e * R + level_off[lvl]) * D, E * R * D)
+                    if var_pc is not None:
+                        var_out = raw["logvar"] if tower == TOWER_CLS else raw["regvar"]
+                        Dv = var_pc.cout // A
+                        self._conv_out(src, B, H, W, var_pc, var_out, (e * R + level_off[lvl]) * Dv, E * R * Dv)
+        return raw, level_off
+
+    # ------------------------------------------------------------------ statistics + post-processing
+    def candidates(self, raw, level_off, anchors, seed, image0):
+        """Q1 means -> scores -> top-k -> decode + covariance."""
+        pc = self.pc
+        S = raw["logits"].shape[1]
+        if S > 1:
+            m_logits = ops.sample_mean_q1(raw["logits"])
+            m_deltas = ops.sample_mean_q1(raw["deltas"])
+            m_logvar = ops.sample_mean_q1(raw["logvar"]) if raw["logvar"] is not None else None
+            m_regvar = ops.sample_mean_q1(raw["regvar"]) if raw["regvar"] is not None else None
+        else:
+            m_logits, m_deltas = raw["logits"][:, 0], raw["deltas"][:, 0]
+            m_logvar = raw["logvar"][:, 0] if raw["logvar"] is not None else None
+            m_regvar = raw["regvar"][:, 0] if raw["regvar"] is not None else None
+            if raw["logits"].shape[0] > 1:
+                m_logits, m_deltas = m_logits.contiguous(), m_deltas.contiguous()
+                m_logvar = m_logvar.contiguous() if m_logvar is not None else None
+                m_regvar = m_regvar.contiguous() if m_regvar is not None else None
+        probs, score, cls = ops.scores(m_logits, m_logvar, level_off, pc.cls_var_num_samples, seed, image0)
+        cand_idx, cand_cnt, seg = ops.topk_levels(score, level_off, pc.topk, pc.score_thresh)
+        cand = ops.decode_cov(m_deltas, m_regvar, raw["deltas"] if S > 1 else None, anchors, probs, score, cls,
+                              cand_idx, cand_cnt, seg, pc.box_num_samples, seed, image0, pc.reg_weights)
+        return cand
+
+    def detections(self, cand, bayes_od, image_hw, out_hw, nms_variant=ops.NMS_AUTO):
+        pc = self.pc
+        return ops.nms_fuse(cand, 1 if bayes_od else 0, pc.nms_thresh, pc.affinity, pc.max_dets, image_hw, out_hw,
+                            nms_variant=nms_variant,
+                            box_merge=0 if pc.box_merge == "bayesian_inference" else 1,
+                            cls_merge=0 if pc.cls_merge == "max_score" else 1)
+
+
+def make_anchors(level_hw, sizes, aspect_ratios, strides, offset=0.0, device="cuda"):
+    """detectron2 DefaultAnchorGenerator semantics (un-vendored dependency, call site reference
+    probabilistic_retinanet.py:101): cell anchors for size outer / ratio inner, w = sqrt(s^2/r),
+    h = r*w, centred; grid shifts row-major, anchor-minor.  Returns (R,4) fp32 on `device`."""
+    out = []
+    for (gh, gw), stride, sz in zip(level_hw, strides, sizes):
+        rows = []
+        for s in sz:
+            area = float(s) ** 2.0
+            for r in aspect_ratios:
+                w = math.sqrt(area / r)
+                h = r * w
+                rows.append([-w / 2.0, -h / 2.0, w / 2.0, h / 2.0])
+        base = torch.tensor(rows, dtype=torch.float32)
+        sx = torch.arange(offset * stride, gw * stride, step=stride, dtype=torch.float32)
+        sy = torch.arange(offset * stride, gh * stride, step=stride, dtype=torch.float32)
+        yy, xx = torch.meshgrid(sy, sx, indexing="ij")
+        xx, yy = xx.reshape(-1), yy.reshape(-1)
+        shifts = torch.stack((xx, yy, xx, yy), dim=1)
+        out.append((shifts.view(-1, 1, 4) + base.view(1, -1, 4)).reshape(-1, 4))
+    return torch.cat(out).to(device).contiguous()

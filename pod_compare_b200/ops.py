@@ -1,0 +1,310 @@
+"""Tensor-level wrappers of the C ABI (one function per `pod_*` entry point).
+
+PyTorch is only the owner of device memory and streams here: each wrapper checks device / dtype /
+contiguity, allocates outputs with torch, and launches the hand-written kernel on the current
+stream.  Reference lines each op replaces are cited in include/podb200.h.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _cabi
+from ._cabi import POD_OUT_HIDDEN, POD_OUT_RAW, ConvArgs, DecodeArgs, Dropout, NmsArgs, check, int_array, ptr, stream_ptr
+
+_launches = 0
+
+
+def launch_count():
+    """Number of libpodb200 kernel launches issued by this process (bench.py's gpu_launches)."""
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _chk(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise _cabi.PodError("%s must be a contiguous CUDA tensor of dtype %s" % (name, dtype))
+    return t
+
+
+def make_dropout(p=0.0, seed=0, image0=0, samples=1, passes=1, pass0=0, tower=0, layer=0, level=0):
+    return Dropout(float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, image0, samples, passes, pass0, tower, layer, level)
+
+
+def pow2_scale(max_abs, target=1024.0):
+    """Largest power of two s with max_abs * s <= target (exact rescaling of fp32 values)."""
+    if not (max_abs > 0.0) or not math.isfinite(max_abs):
+        return 1.0
+    return float(2.0 ** math.floor(math.log2(target / max_abs)))
+
+
+# ---------------------------------------------------------------------------------------------------
+def philox_dropout_mask(H, W, Cn, seed, image, sample, pass_, tower, layer, level, p):
+    lib = _cabi.require_device()
+    out = torch.empty((H, W, Cn), dtype=torch.uint8, device="cuda")
+    check(lib.pod_philox_dropout_mask(ptr(out), H, W, Cn, seed, image, sample, pass_, tower, layer, level, float(p),
+                                      stream_ptr()), "pod_philox_dropout_mask")
+    _count()
+    return out
+
+
+def philox_logit_normals(draws, n_anchor, K, seed, image, level):
+    lib = _cabi.require_device()
+    out = torch.empty((draws, n_anchor, K), dtype=torch.float32, device="cuda")
+    check(lib.pod_philox_logit_normals(ptr(out), draws, n_anchor, K, seed, image, level, stream_ptr()),
+          "pod_philox_logit_normals")
+    _count()
+    return out
+
+
+def philox_box_normals(anchor_ids, draws, seed, image):
+    lib = _cabi.require_device()
+    ids = _chk(anchor_ids, torch.int64, "anchor_ids")
+    out = torch.empty((draws, ids.numel(), 4), dtype=torch.float32, device="cuda")
+    check(lib.pod_philox_box_normals(ptr(out), ptr(ids), ids.numel(), draws, seed, image, stream_ptr()),
+          "pod_philox_box_normals")
+    _count()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+def nchw_to_nhwc_split(x, scale):
+    lib = _cabi.require_device()
+    _chk(x, torch.float32, "x")
+    NB, Cn, H, W = x.shape
+    hi = torch.empty((NB, H, W, Cn), dtype=torch.float16, device=x.device)
+    lo = torch.empty_like(hi)
+    check(lib.pod_nchw_to_nhwc_split(ptr(x), NB, Cn, H, W, scale, ptr(hi), ptr(lo), stream_ptr()), "pod_nchw_to_nhwc_split")
+    _count()
+    return hi, lo
+
+
+def nchw_to_nhwc_f32(x):
+    lib = _cabi.require_device()
+    _chk(x, torch.float32, "x")
+    NB, Cn, H, W = x.shape
+    out = torch.empty((NB, H, W, Cn), dtype=torch.float32, device=x.device)
+    check(lib.pod_nchw_to_nhwc_f32(ptr(x), NB, Cn, H, W, ptr(out), stream_ptr()), "pod_nchw_to_nhwc_f32")
+    _count()
+    return out
+
+
+def pack_conv_weight(w, cout_pad, scale):
+    lib = _cabi.require_device()
+    _chk(w, torch.float32, "w")
+    cout, cin = w.shape[0], w.shape[1]
+    assert tuple(w.shape[2:]) == (3, 3)
+    hi = torch.empty((cout_pad, 9 * cin), dtype=torch.float16, device=w.device)
+    lo = torch.empty_like(hi)
+    check(lib.pod_pack_conv_weight(ptr(w), cout, cin, cout_pad, scale, ptr(hi), ptr(lo), stream_ptr()), "pod_pack_conv_weight")
+    _count()
+    return hi, lo
+
+
+def pack_conv_weight_f32(w, cout_pad):
+    lib = _cabi.require_device()
+    _chk(w, torch.float32, "w")
+    cout, cin = w.shape[0], w.shape[1]
+    out = torch.empty((9 * cin, cout_pad), dtype=torch.float32, device=w.device)
+    check(lib.pod_pack_conv_weight_f32(ptr(w), cout, cin, cout_pad, ptr(out), stream_ptr()), "pod_pack_conv_weight_f32")
+    _count()
+    return out
+
+
+def mask_expand_split(x, drop, scale, out_hi=None, out_lo=None):
+    """x (NB, HW, C) fp32 -> (NB*samples*passes, HW, C) fp16 split pair."""
+    lib = _cabi.require_device()
+    _chk(x, torch.float32, "x")
+    NB, HW, Cn = x.shape
+    reps = drop.samples * drop.passes
+    if out_hi is None:
+        out_hi = torch.empty((NB * reps, HW, Cn), dtype=torch.float16, device=x.device)
+        out_lo = torch.empty_like(out_hi)
+    assert out_hi.numel() >= NB * reps * HW * Cn and out_lo.numel() >= NB * reps * HW * Cn
+    check(lib.pod_mask_expand_split(ptr(x), NB, HW, Cn, C.byref(drop), scale, ptr(out_hi), ptr(out_lo), stream_ptr()),
+          "pod_mask_expand_split")
+    _count()
+    return out_hi, out_lo
+
+
+def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias, Cout, Cout_pad, mode, relu,
+               out_hi=None, out_lo=None, out_scale=1.0, out_f32=None, out_map_stride=0, out_pixel_stride=0,
+               drop=None, in_map_stride=None, in_offset=0, out_offset=0):
+    """Raw-pointer launch of the tcgen05 convolution. `in_offset`/`out_offset` are ELEMENT offsets
+    into in_hi/in_lo and out_f32."""
+    lib = _cabi.require_device()
+    a = ConvArgs()
+    esz = 2
+    a.in_hi = in_hi.data_ptr() + in_offset * esz
+    a.in_lo = in_lo.data_ptr() + in_offset * esz
+    a.in_map_stride = in_map_stride if in_map_stride is not None else H * W * Cin
+    a.in_scale = in_scale
+    a.NB, a.H, a.W, a.Cin = NB, H, W, Cin
+    a.w_hi, a.w_lo, a.w_scale = w_hi.data_ptr(), w_lo.data_ptr(), w_scale
+    a.bias = bias.data_ptr()
+    a.Cout, a.Cout_pad, a.mode, a.relu = Cout, Cout_pad, mode, int(relu)
+    a.out_hi = out_hi.data_ptr() if out_hi is not None else None
+    a.out_lo = out_lo.data_ptr() if out_lo is not None else None
+    a.out_scale = out_scale
+    a.out_f32 = (out_f32.data_ptr() + out_offset * 4) if out_f32 is not None else None
+    a.out_map_stride, a.out_pixel_stride = out_map_stride, out_pixel_stride
+    a.drop = drop if drop is not None else make_dropout()
+    check(lib.pod_conv3x3_tc(C.byref(a), stream_ptr()), "pod_conv3x3_tc")
+    _count()
+
+
+def conv3x3_tc_status():
+    lib = _cabi.require_device()
+    v = C.c_int(0)
+    check(lib.pod_conv3x3_tc_status(C.byref(v)), "pod_conv3x3_tc_status")
+    return v.value
+
+
+def set_conv_kblock(bk):
+    check(_cabi.load_library().pod_conv3x3_tc_set_kblock(int(bk)), "pod_conv3x3_tc_set_kblock")
+
+
+def conv3x3_simt(x, w_kc, bias, Cout, Cout_pad, relu, drop=None, out=None, out_map_stride=None, out_pixel_stride=None,
+                 out_offset=0):
+    lib = _cabi.require_device()
+    _chk(x, torch.float32, "x")
+    NB, H, W, Cin = x.shape
+    if out is None:
+        out = torch.empty((NB, H * W, Cout), dtype=torch.float32, device=x.device)
+        out_map_stride, out_pixel_stride = H * W * Cout, Cout
+    check(lib.pod_conv3x3_simt(ptr(x), NB, H, W, Cin, ptr(w_kc), ptr(bias), Cout, Cout_pad, int(relu),
+                               C.byref(drop) if drop is not None else None,
+                               C.c_void_p(out.data_ptr() + out_offset * 4), out_map_stride, out_pixel_stride, stream_ptr()),
+          "pod_conv3x3_simt")
+    _count()
+    return out
+
+
+def sample_mean_q1(x):
+    """x (B, S, ...) -> (B, ...) with the reference's Q1 weighting."""
+    lib = _cabi.require_device()
+    _chk(x, torch.float32, "x")
+    B, S = x.shape[0], x.shape[1]
+    n = x[0, 0].numel()
+    out = torch.empty((B,) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    check(lib.pod_sample_mean_q1(ptr(x), B, S, n, ptr(out), stream_ptr()), "pod_sample_mean_q1")
+    _count()
+    return out
+
+
+def scores(logits, logvar, level_off, draws, seed, image0):
+    """logits/logvar (B,R,K) -> probs (B,R,K), score (B,R), cls (B,R) int32."""
+    lib = _cabi.require_device()
+    _chk(logits, torch.float32, "logits")
+    if logvar is not None:
+        _chk(logvar, torch.float32, "logvar")
+    B, R, K = logits.shape
+    probs = torch.empty_like(logits)
+    score = torch.empty((B, R), dtype=torch.float32, device=logits.device)
+    cls = torch.empty((B, R), dtype=torch.int32, device=logits.device)
+    check(lib.pod_scores(ptr(logits), ptr(logvar), B, R, K, len(level_off) - 1, int_array(level_off), draws, seed, image0,
+                         ptr(probs), ptr(score), ptr(cls), stream_ptr()), "pod_scores")
+    _count()
+    return probs, score, cls
+
+
+def seg_offsets(level_off, topk):
+    seg = [0]
+    for l in range(len(level_off) - 1):
+        seg.append(seg[-1] + min(topk, level_off[l + 1] - level_off[l]))
+    return seg
+
+
+def topk_levels(score, level_off, topk, thresh):
+    lib = _cabi.require_device()
+    _chk(score, torch.float32, "score")
+    B, R = score.shape
+    seg = seg_offsets(level_off, topk)
+    cap = seg[-1]
+    cand_idx = torch.zeros((B, cap), dtype=torch.int32, device=score.device)
+    cand_cnt = torch.zeros((B, len(level_off) - 1), dtype=torch.int32, device=score.device)
+    check(lib.pod_topk_levels(ptr(score), B, R, len(level_off) - 1, int_array(level_off), int_array(seg), topk, thresh,
+                              ptr(cand_idx), ptr(cand_cnt), stream_ptr()), "pod_topk_levels")
+    _count()
+    return cand_idx, cand_cnt, seg
+
+
+def decode_cov(mean_delta, mean_regvar, sample_delta, anchors, probs, score, cls, cand_idx, cand_cnt, seg, box_draws,
+               seed, image0, reg_weights):
+    lib = _cabi.require_device()
+    B, R, K = probs.shape
+    cap = seg[-1]
+    dev = probs.device
+    out = {
+        "boxes": torch.zeros((B, cap, 4), dtype=torch.float32, device=dev),
+        "cov": torch.zeros((B, cap, 4, 4), dtype=torch.float32, device=dev),
+        "scores": torch.zeros((B, cap), dtype=torch.float32, device=dev),
+        "classes": torch.zeros((B, cap), dtype=torch.int32, device=dev),
+        "probs": torch.zeros((B, cap, K), dtype=torch.float32, device=dev),
+        "count": torch.zeros((B,), dtype=torch.int32, device=dev),
+        "anchor": torch.zeros((B, cap), dtype=torch.int32, device=dev),
+    }
+    a = DecodeArgs()
+    a.mean_delta = _chk(mean_delta, torch.float32, "mean_delta").data_ptr()
+    a.mean_regvar = _chk(mean_regvar, torch.float32, "mean_regvar").data_ptr() if mean_regvar is not None else None
+    a.cov_dims = mean_regvar.shape[-1] if mean_regvar is not None else 4
+    a.sample_delta = _chk(sample_delta, torch.float32, "sample_delta").data_ptr() if sample_delta is not None else None
+    a.S = sample_delta.shape[1] if sample_delta is not None else 1
+    a.anchors = _chk(anchors, torch.float32, "anchors").data_ptr()
+    a.probs, a.score, a.cls = probs.data_ptr(), score.data_ptr(), cls.data_ptr()
+    a.cand_idx, a.cand_cnt = cand_idx.data_ptr(), cand_cnt.data_ptr()
+    a.B, a.R, a.K, a.n_levels, a.cap = B, R, K, len(seg) - 1, cap
+    seg_arr = int_array(seg)
+    a.seg_off_host = seg_arr
+    a.box_draws, a.seed, a.image0 = box_draws, int(seed) & 0xFFFFFFFFFFFFFFFF, image0
+    a.wx, a.wy, a.ww, a.wh = [float(v) for v in reg_weights]
+    a.out_boxes, a.out_cov = out["boxes"].data_ptr(), out["cov"].data_ptr()
+    a.out_scores, a.out_classes = out["scores"].data_ptr(), out["classes"].data_ptr()
+    a.out_probs, a.out_count, a.out_anchor = out["probs"].data_ptr(), out["count"].data_ptr(), out["anchor"].data_ptr()
+    check(lib.pod_decode_cov(C.byref(a), stream_ptr()), "pod_decode_cov")
+    _count()
+    out["has_cov"] = (mean_regvar is not None) or (sample_delta is not None and a.S > 1)
+    return out
+
+
+NMS_VANILLA, NMS_TRICK, NMS_AUTO = 0, 1, 2
+
+
+def nms_fuse(cand, mode, nms_thresh, affinity, max_dets, in_hw, out_hw, nms_variant=NMS_AUTO, box_merge=0, cls_merge=0):
+    """cand: dict with boxes (B,cap,4), cov (B,cap,4,4), scores, classes (int32), probs, count, has_cov."""
+    lib = _cabi.require_device()
+    B, cap, K = cand["probs"].shape
+    dev = cand["probs"].device
+    out = {
+        "boxes": torch.zeros((B, max_dets, 4), dtype=torch.float32, device=dev),
+        "cov": torch.zeros((B, max_dets, 4, 4), dtype=torch.float32, device=dev),
+        "scores": torch.zeros((B, max_dets), dtype=torch.float32, device=dev),
+        "classes": torch.zeros((B, max_dets), dtype=torch.int32, device=dev),
+        "probs": torch.zeros((B, max_dets, K), dtype=torch.float32, device=dev),
+        "count": torch.zeros((B,), dtype=torch.int32, device=dev),
+        "keep": torch.zeros((B, max_dets), dtype=torch.int32, device=dev),
+        "keep_count": torch.zeros((B,), dtype=torch.int32, device=dev),
+    }
+    a = NmsArgs()
+    a.boxes = _chk(cand["boxes"], torch.float32, "boxes").data_ptr()
+    a.cov = _chk(cand["cov"], torch.float32, "cov").data_ptr()
+    a.scores = _chk(cand["scores"], torch.float32, "scores").data_ptr()
+    a.classes = _chk(cand["classes"], torch.int32, "classes").data_ptr()
+    a.probs = _chk(cand["probs"], torch.float32, "probs").data_ptr()
+    a.count = _chk(cand["count"], torch.int32, "count").data_ptr()
+    a.B, a.cap, a.K = B, cap, K
+    a.has_cov = int(bool(cand.get("has_cov", True)))
+    a.mode, a.nms_variant, a.box_merge, a.cls_merge = mode, nms_variant, box_merge, cls_merge
+    a.nms_thresh, a.affinity, a.max_dets = float(nms_thresh), float(affinity), max_dets
+    a.in_h, a.in_w, a.out_h, a.out_w = int(in_hw[0]), int(in_hw[1]), int(out_hw[0]), int(out_hw[1])
+    a.det_boxes, a.det_cov = out["boxes"].data_ptr(), out["cov"].data_ptr()
+    a.det_scores, a.det_classes = out["scores"].data_ptr(), out["classes"].data_ptr()
+    a.det_probs, a.det_count = out["probs"].data_ptr(), out["count"].data_ptr()
+    a.keep, a.keep_count = out["keep"].data_ptr(), out["keep_count"].data_ptr()
+    check(lib.pod_nms_fuse(C.byref(a), stream_ptr()), "pod_nms_fuse")
+    _count()
+    return out

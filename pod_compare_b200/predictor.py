@@ -1,0 +1,240 @@
+"""Reference-facing plugin surface: `build_predictor(cfg)` -> predictor with `__call__(input_im)`.
+
+Same names, argument meaning and error behaviour as the reference
+(src/probabilistic_inference/probabilistic_inference.py:20-33, 36-111, 169-176, 390-407, 430-443,
+483-505, 536-636), with the arithmetic moved to libpodb200 and two batched entry points added for the
+B200 path: `predict_batch(list_of_inputs)` and `infer_from_features(feats, ...)`.
+
+Input convention: each `input_im` is the list-of-one-dict of the detectron2 data loader
+({"image": (3,H,W) tensor, "height", "width", "image_id"}, src/apply_net.py:88-96).  The ResNet-FPN
+backbone is upstream of the path rebuilt here: a dict may carry precomputed
+"features" (list of 5 (1|B,256,Hl,Wl) tensors); otherwise `predictor.backbone` (any callable mapping
+the preprocessed image batch to the 5 FPN maps) must be set.
+"""
+import os
+
+import torch
+
+from . import _cabi, engine, ops
+from .engine import HeadEngine, HeadWeights, PathConfig
+from .structures import Boxes, Instances
+
+SUPPORTED_PRE_NMS_MODES = ("standard_nms", "mc_dropout_ensembles", "ensembles", "bayes_od")
+
+
+def build_predictor(cfg):
+    """reference probabilistic_inference.py:20-33."""
+    if cfg.MODEL.META_ARCHITECTURE == 'ProbabilisticRetinaNet':
+        return RetinaNetProbabilisticPredictor(cfg)
+    raise ValueError('Invalid meta-architecture {}.'.format(cfg.MODEL.META_ARCHITECTURE))
+
+
+class _ModelFacade:
+    """The attributes of `predictor.model` the reference reads (probabilistic_inference.py:207,294,
+    300,304,326,407,449,621): both detectron2 API generations are exposed."""
+
+    def __init__(self, cfg, device):
+        r = cfg.MODEL.RETINANET
+        pm = cfg.MODEL.PROBABILISTIC_MODELING
+        self.num_classes = r.NUM_CLASSES
+        self.in_features = self.head_in_features = list(r.IN_FEATURES)
+        self.test_score_thresh = self.score_threshold = r.SCORE_THRESH_TEST
+        self.test_topk_candidates = self.topk_candidates = r.TOPK_CANDIDATES_TEST
+        self.test_nms_thresh = self.nms_threshold = r.NMS_THRESH_TEST
+        self.max_detections_per_image = cfg.TEST.DETECTIONS_PER_IMAGE
+        self.cls_var_num_samples = pm.CLS_VAR_LOSS.NUM_SAMPLES
+        self.bbox_cov_num_samples = pm.BBOX_COV_LOSS.NUM_SAMPLES
+        self.compute_cls_var = pm.CLS_VAR_LOSS.NAME != 'none'
+        self.compute_bbox_cov = pm.BBOX_COV_LOSS.NAME != 'none'
+        self.bbox_cov_dims = 4 if pm.BBOX_COV_LOSS.COVARIANCE_TYPE == 'diagonal' else 10
+        self.dropout_rate = pm.DROPOUT_RATE
+        self.use_dropout = self.dropout_rate != 0.0
+        self.device = device
+        self.training = False
+
+    def train(self):
+        self.training = True
+
+    def eval(self):
+        self.training = False
+
+
+class ProbabilisticPredictor:
+    """reference probabilistic_inference.py:36-111 (construction, mode dispatch, final rescale)."""
+
+    def __init__(self, cfg):
+        _cabi.require_device()          # fail loudly: no CPU / eager fallback exists for this path
+        self.cfg = cfg.clone()
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.model = _ModelFacade(self.cfg, self.device)
+        self.model_list = []
+        self.inference_mode = self.cfg.PROBABILISTIC_INFERENCE.INFERENCE_MODE
+        self.mc_dropout_enabled = self.cfg.PROBABILISTIC_INFERENCE.MC_DROPOUT.ENABLE
+        self.num_mc_dropout_runs = self.cfg.PROBABILISTIC_INFERENCE.MC_DROPOUT.NUM_RUNS
+        if self.mc_dropout_enabled:
+            self.model.train()
+        else:
+            self.model.eval()
+        self.backbone = None
+        self.rng_seed = int(self.cfg.SEED) if int(self.cfg.SEED) >= 0 else 0
+        self.weight_sets = []
+        self._engine = None
+        self._anchor_cache = {}
+        # checkpoints (probabilistic_inference.py:58-84): <OUTPUT_DIR>/model_final.pth, or the sibling
+        # random_seed_<s> directories for ensembles; absent files leave the weights to load_weight_sets().
+        paths = []
+        if self.inference_mode == 'ensembles':
+            for s in self.cfg.PROBABILISTIC_INFERENCE.ENSEMBLES.RANDOM_SEED_NUMS:
+                paths.append(os.path.join(os.path.split(self.cfg.OUTPUT_DIR)[0], 'random_seed_' + str(s), 'model_final.pth'))
+        else:
+            paths.append(os.path.join(self.cfg.OUTPUT_DIR, 'model_final.pth'))
+        if all(os.path.isfile(p) for p in paths):
+            sds = []
+            for p in paths:
+                sd = torch.load(p, map_location="cpu")
+                sds.append(sd.get("model", sd))
+            self.load_weight_sets(sds)
+
+    # ---------------------------------------------------------------------------------------------
+    def path_config(self):
+        cfg, m = self.cfg, self.model
+        pi = cfg.PROBABILISTIC_INFERENCE
+        ratios = cfg.MODEL.ANCHOR_GENERATOR.ASPECT_RATIOS
+        return PathConfig(
+            num_classes=m.num_classes,
+            num_anchors=len(cfg.MODEL.ANCHOR_GENERATOR.SIZES[0]) * len(ratios[0]),
+            dropout_rate=m.dropout_rate, cls_var=m.compute_cls_var, bbox_cov=m.compute_bbox_cov,
+            cov_dims=m.bbox_cov_dims, cls_var_num_samples=m.cls_var_num_samples, box_num_samples=1000,
+            topk=m.test_topk_candidates, score_thresh=m.test_score_thresh, nms_thresh=m.test_nms_thresh,
+            max_dets=m.max_detections_per_image, reg_weights=tuple(cfg.MODEL.RETINANET.BBOX_REG_WEIGHTS),
+            affinity=pi.AFFINITY_THRESHOLD, box_merge=pi.BAYES_OD.BOX_MERGE_MODE, cls_merge=pi.BAYES_OD.CLS_MERGE_MODE)
+
+    def load_weight_sets(self, state_dicts):
+        """One state dict (reference key names), or E of them for INFERENCE_MODE 'ensembles'."""
+        if isinstance(state_dicts, dict):
+            state_dicts = [state_dicts]
+        m = self.model
+        self.weight_sets = [HeadWeights(sd, m.use_dropout, m.compute_cls_var, m.compute_bbox_cov,
+                                        self.cfg.MODEL.RETINANET.NUM_CONVS, self.device) for sd in state_dicts]
+        self._engine = HeadEngine(self.path_config(), self.weight_sets, self.device)
+        return self
+
+    def _anchors(self, level_hw):
+        key = tuple(level_hw)
+        if key not in self._anchor_cache:
+            ag = self.cfg.MODEL.ANCHOR_GENERATOR
+            sizes = ag.SIZES if len(ag.SIZES) == len(level_hw) else list(ag.SIZES) * len(level_hw)
+            self._anchor_cache[key] = engine.make_anchors(level_hw, sizes, ag.ASPECT_RATIOS[0], (8, 16, 32, 64, 128),
+                                                          ag.OFFSET, self.device)
+        return self._anchor_cache[key]
+
+    # ---------------------------------------------------------------------------------------------
+    def __call__(self, input_im):
+        """reference probabilistic_inference.py:86-111: one image in, Instances out."""
+        if self.inference_mode not in ('standard_nms', 'mc_dropout_ensembles', 'anchor_statistics', 'ensembles', 'bayes_od'):
+            raise ValueError('Invalid inference mode {}.'.format(self.inference_mode))
+        return self.predict_batch([input_im])[0]
+
+    def predict_batch(self, inputs):
+        """B independent single-image problems in one pass. `inputs` is a list of
+        reference-style `input_im` lists."""
+        dicts = [x[0] if isinstance(x, (list, tuple)) else x for x in inputs]
+        hw = [tuple(d["image"].shape[-2:]) if "image" in d else tuple(d["image_hw"]) for d in dicts]
+        if len(set(hw)) != 1:
+            raise ValueError("predict_batch needs images of one size; got {}".format(sorted(set(hw))))
+        out_hw = [(d.get("height", hw[0][0]), d.get("width", hw[0][1])) for d in dicts]
+        if len(set(out_hw)) != 1:
+            raise ValueError("predict_batch needs one output resolution per batch")
+        if all("features" in d for d in dicts):
+            n_lvl = len(dicts[0]["features"])
+            feats = [torch.cat([d["features"][l].reshape((-1,) + tuple(d["features"][l].shape[-3:])) for d in dicts], 0)
+                     for l in range(n_lvl)]
+        else:
+            if self.backbone is None:
+                raise _cabi.PodError("no 'features' in the inputs and predictor.backbone is not set "
+                                     "(the ResNet-FPN backbone is upstream of this path)")
+            feats = self.backbone([d["image"] for d in dicts])
+        ids = [d.get("image_id", i) for i, d in enumerate(dicts)]
+        image0 = ids[0] if all(isinstance(i, int) for i in ids) and ids == list(range(ids[0], ids[0] + len(ids))) else 0
+        return self.infer_from_features(feats, hw[0], out_hw[0], image0=image0)
+
+    def infer_from_features(self, feats, image_hw, out_hw=None, image0=0, seed=None, return_raw=False,
+                            return_candidates=False):
+        """feats: list over FPN levels of (B,256,Hl,Wl) fp32 tensors (host or device).
+        image_hw: size of the network input (Instances.image_size before rescale,
+        inference_utils.py:39-41); out_hw: requested output resolution (:374-397)."""
+        if self._engine is None:
+            raise _cabi.PodError("no weights loaded: call load_weight_sets(state_dicts) first")
+        mode = self.inference_mode
+        pi = self.cfg.PROBABILISTIC_INFERENCE
+        if mode == 'anchor_statistics':
+            raise NotImplementedError("anchor_statistics post-processing is outside the rebuilt path (SURVEY 8f rank 1)")
+        if mode == 'mc_dropout_ensembles' and pi.ENSEMBLES_DROPOUT.BOX_MERGE_MODE != 'pre_nms':
+            raise NotImplementedError("post_nms MC-dropout merging is outside the rebuilt path (SURVEY 8f rank 1)")
+        if mode == 'ensembles' and pi.ENSEMBLES.BOX_MERGE_MODE != 'pre_nms':
+            raise NotImplementedError("post_nms ensemble merging is outside the rebuilt path (SURVEY 8f rank 1)")
+        if mode not in SUPPORTED_PRE_NMS_MODES:
+            raise ValueError('Invalid inference mode {}.'.format(mode))
+        out_hw = tuple(out_hw) if out_hw is not None else tuple(image_hw)
+        seed = self.rng_seed if seed is None else seed
+        eng = self._engine
+        feats = [f.to(self.device, dtype=torch.float32, non_blocking=True).contiguous() for f in feats]
+        level_hw = [tuple(f.shape[-2:]) for f in feats]
+        anchors = self._anchors(level_hw)
+        if mode == 'ensembles':
+            if len(self.weight_sets) != len(pi.ENSEMBLES.RANDOM_SEED_NUMS):
+                raise _cabi.PodError("ensembles mode needs one weight set per RANDOM_SEED_NUMS entry")
+            raw, level_off = eng.head_eval(feats)
+        elif self.mc_dropout_enabled and self.num_mc_dropout_runs > 1:
+            if not self.model.use_dropout:
+                raise _cabi.PodError("MC_DROPOUT.ENABLE with DROPOUT_RATE == 0 is not supported")
+            raw, level_off = eng.head_mc(feats, self.num_mc_dropout_runs, seed, image0)
+        else:
+            raw, level_off = eng.head_eval(feats, members=[0])
+        cand = eng.candidates(raw, level_off, anchors, seed, image0)
+        det = eng.detections(cand, mode == 'bayes_od', image_hw, out_hw)
+        res = self._to_instances(det, out_hw)
+        if return_raw or return_candidates:
+            return res, (raw if return_raw else None), cand, det
+        return res
+
+    def _to_instances(self, det, out_hw):
+        counts = det["count"].cpu().tolist()
+        out = []
+        for b, n in enumerate(counts):
+            inst = Instances((int(out_hw[0]), int(out_hw[1])))
+            inst.pred_boxes = Boxes(det["boxes"][b, :n])
+            inst.scores = det["scores"][b, :n]
+            inst.pred_classes = det["classes"][b, :n].to(torch.int64)
+            inst.pred_cls_probs = det["probs"][b, :n]
+            inst.pred_boxes_covariance = det["cov"][b, :n]
+            out.append(inst)
+        return out
+
+
+class RetinaNetProbabilisticPredictor(ProbabilisticPredictor):
+    """reference probabilistic_inference.py:169-636; the five `post_processing_*` entry points keep
+    their names and accept the same `input_im`."""
+
+    def post_processing_standard_nms(self, input_im):
+        return self._single(input_im, 'standard_nms')
+
+    def post_processing_mc_dropout_ensembles(self, input_im):
+        return self._single(input_im, 'mc_dropout_ensembles')
+
+    def post_processing_ensembles(self, input_im, model_list=None):
+        return self._single(input_im, 'ensembles')
+
+    def post_processing_bayes_od(self, input_im):
+        return self._single(input_im, 'bayes_od')
+
+    def post_processing_anchor_statistics(self, input_im):
+        raise NotImplementedError("anchor_statistics post-processing is outside the rebuilt path (SURVEY 8f rank 1)")
+
+    def _single(self, input_im, mode):
+        saved = self.inference_mode
+        self.inference_mode = mode
+        try:
+            return self.predict_batch([input_im])[0]
+        finally:
+            self.inference_mode = saved

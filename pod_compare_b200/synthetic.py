@@ -79,7 +79,7 @@ def make_planted_candidates(seed, num_gt=20, per_gt=(1, 40), image_hw=(720, 1280
                             jitter=1.5, score_margin=1e-3):
     """Planted-cluster candidate set for stage-isolated NMS / BayesOD tests:
     jittered copies of `num_gt` boxes so that IoU>0.9 clusters of several sizes exist;
-    scores are distinct with at least `score_margin` spacing.
+    scores are distinct, spaced by min(score_margin, 0.93/M).
     Returns boxes (M,4), cov (M,4,4) SPD, scores (M,), classes (M,) int64, prob vectors (M,K)."""
     g = torch.Generator().manual_seed(2024 + int(seed))
     H, W = image_hw
@@ -105,8 +105,7 @@ def make_planted_candidates(seed, num_gt=20, per_gt=(1, 40), image_hw=(720, 1280
     boxes, classes = boxes[perm], classes[perm]
     # distinct scores with a guaranteed margin, in (0.05, 1)
     ranks = torch.randperm(M, generator=g).float()
-    scores = 0.06 + ranks * max(score_margin, 0.9 / max(M, 1))
-    scores = scores.clamp(max=0.999).float()
+    scores = (0.06 + ranks * min(score_margin, 0.93 / max(M, 1))).float()
     probs = torch.rand((M, num_classes), generator=g) * 0.04
     probs[torch.arange(M), classes] = scores
     A = torch.randn((M, 4, 4), generator=g) * 1.5

@@ -1,0 +1,97 @@
+"""CPU-side checks of the boundary: the library builds, loads, exports every symbol that
+include/podb200.h declares, the ctypes mirrors match the C struct layouts, argument validation
+returns error codes (no compute without a GPU), and the product refuses to run without a device."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "podb200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from pod_compare_b200 import build, _cabi
+    build.build()
+    return _cabi.load_library()
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pod_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from pod_compare_b200 import _cabi
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(_cabi.EXPORTS) == names
+
+
+def test_struct_layouts_match_header(tmp_path):
+    from pod_compare_b200 import _cabi
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n",'
+                   'sizeof(pod_dropout),sizeof(pod_conv_args),sizeof(pod_decode_args),sizeof(pod_nms_args),'
+                   'offsetof(pod_conv_args,drop),offsetof(pod_decode_args,out_anchor),offsetof(pod_nms_args,keep_count));return 0;}\n' % HEADER)
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    want = [ctypes.sizeof(_cabi.Dropout), ctypes.sizeof(_cabi.ConvArgs), ctypes.sizeof(_cabi.DecodeArgs),
+            ctypes.sizeof(_cabi.NmsArgs), _cabi.ConvArgs.drop.offset, _cabi.DecodeArgs.out_anchor.offset,
+            _cabi.NmsArgs.keep_count.offset]
+    assert got == want
+
+
+def test_error_codes_and_messages(lib):
+    assert lib.pod_version() == 1
+    rc = lib.pod_conv3x3_tc(None, None)
+    assert rc < 0 and b"null args" in lib.pod_last_error()
+    rc = lib.pod_sample_mean_q1(None, 0, 0, 0, None, None)
+    assert rc < 0 and b"pod_sample_mean_q1" in lib.pod_last_error()
+    rc = lib.pod_conv3x3_tc_set_kblock(48)
+    assert rc < 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_fails_loudly_without_gpu():
+    from pod_compare_b200 import _cabi
+    from pod_compare_b200.predictor import build_predictor
+    from oracle import cases as C
+    with pytest.raises(_cabi.PodError):
+        build_predictor(C.build_cfg("baseline_std"))
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "pod_compare_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_reference_config_yaml_surface():
+    """The reference's own YAML files (model + inference config, two-stage merge) load unchanged
+    when present; the key set the path reads exists with the reference defaults."""
+    from pod_compare_b200.config import get_cfg, setup_config
+    cfg = get_cfg()
+    assert cfg.PROBABILISTIC_INFERENCE.AFFINITY_THRESHOLD == 0.7
+    assert cfg.PROBABILISTIC_INFERENCE.ENSEMBLES.RANDOM_SEED_NUMS == [0, 1000, 2000, 3000, 4000]
+    assert cfg.MODEL.PROBABILISTIC_MODELING.BBOX_COV_LOSS.NUM_SAMPLES == 1000
+    d = "/root/reference/src/configs"
+    if os.path.isdir(d):
+        c = setup_config(os.path.join(d, "BDD-Detection/retinanet/retinanet_R_50_FPN_1x_reg_cls_var_dropout.yaml"),
+                         os.path.join(d, "Inference/bayes_od_mc_dropout.yaml"))
+        assert c.MODEL.RETINANET.NUM_CLASSES == 7 and c.MODEL.PROBABILISTIC_MODELING.DROPOUT_RATE == 0.2
+        assert c.PROBABILISTIC_INFERENCE.INFERENCE_MODE == "bayes_od" and c.PROBABILISTIC_INFERENCE.MC_DROPOUT.NUM_RUNS == 10
+        assert c.PROBABILISTIC_INFERENCE.BAYES_OD.CLS_MERGE_MODE == "max_score"
+        assert abs(c.MODEL.ANCHOR_GENERATOR.SIZES[0][1] - 32 * 2 ** (1 / 3)) < 1e-9
+        assert c.is_frozen()

@@ -1,0 +1,220 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (pod_compare_b200.ops).
+
+Tolerances (stated per SURVEY 8c / BASELINE north_star "within 1e-4 rel fp32, survivor indices
+bit-exact"):
+  * integer / index / mask outputs ........ bit-exact
+  * Philox normals ........................ |d| <= 2e-6 (fp32 log/sincos a few ulp from the fp64-rounded oracle)
+  * convolutions .......................... max|err| <= 1e-5 * max|ref| against an fp64 convolution
+    (the fp32 CPU convolution the reference runs is itself ~1e-6 from fp64)
+  * scores / boxes ........................ rtol 1e-4 (observed ~1e-6)
+  * covariances ........................... max|err| <= 1e-4 * max|cov| per matrix
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import philox
+from oracle import podref as O
+from pod_compare_b200 import engine, ops, synthetic as S
+from tests import gpu_util as G
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    from pod_compare_b200 import _cabi
+    _cabi.require_device()      # raises (test error) rather than skipping: no silent fallback
+
+
+# ------------------------------------------------------------------------------------------ RNG
+def test_philox_dropout_mask_bit_exact():
+    for (H, W, C, p) in ((6, 10, 256, 0.2), (8, 16, 64, 0.5), (3, 5, 256, 0.05)):
+        ref = philox.dropout_keep_mask(77, 3, 5, 1, 1, 2, 4, H, W, C, p)
+        got = ops.philox_dropout_mask(H, W, C, 77, 3, 5, 1, 1, 2, 4, p).cpu().numpy().astype(bool)
+        assert np.array_equal(ref, got)
+
+
+def test_philox_normals_close():
+    ref = philox.logit_normals(5, 2, 3, 10, 333, 7)
+    got = ops.philox_logit_normals(10, 333, 7, 5, 2, 3).cpu().numpy()
+    assert np.abs(ref - got).max() <= 2e-6
+    ids = np.array([0, 5, 17, 184139, 99999], dtype=np.int64)
+    ref = philox.box_normals((1 << 40) + 9, 6, ids, 100)
+    got = ops.philox_box_normals(torch.from_numpy(ids).cuda(), 100, (1 << 40) + 9, 6).cpu().numpy()
+    assert np.abs(ref - got).max() <= 2e-6
+    assert abs(float(got.mean())) < 0.2 and 0.8 < float(got.std()) < 1.2
+
+
+# ------------------------------------------------------------------------------------------ prep
+def test_layout_and_split_roundtrip():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((2, 256, 5, 7), generator=g) * 3
+    hi, lo = ops.nchw_to_nhwc_split(x.cuda(), 16.0)
+    rec = ((hi.float() + lo.float()) / 16.0).permute(0, 3, 1, 2).cpu()
+    assert G.rel_err(rec, x) < 1e-6
+    f32 = ops.nchw_to_nhwc_f32(x.cuda()).permute(0, 3, 1, 2).cpu()
+    assert torch.equal(f32, x)
+
+
+def test_sample_mean_q1_bit_exact():
+    g = torch.Generator().manual_seed(1)
+    for S_ in (1, 2, 5, 30):
+        x = torch.randn((3, S_, 1001), generator=g)
+        ref = O.quirk_mean([[x[:, s]] for s in range(S_)])[0] if S_ > 1 else x[:, 0]
+        got = ops.sample_mean_q1(x.cuda()).cpu()
+        assert torch.equal(got, ref), S_
+
+
+def test_mask_expand_matches_oracle():
+    g = torch.Generator().manual_seed(2)
+    H, W, C, N = 4, 6, 256, 3
+    x = torch.relu(torch.randn((2, H * W, C), generator=g))
+    d = ops.make_dropout(0.2, 9, 4, N, 2, 0, 1, 0, 2)
+    hi, lo = ops.mask_expand_split(x.cuda(), d, 16.0)
+    rec = ((hi.float() + lo.float()) / 16.0).cpu().view(2, N, 2, H, W, C)
+    drop = O.DropoutSource("philox", 0.2, 9, 0)
+    for b in range(2):
+        for s in range(N):
+            for ps in range(2):
+                drop.image = 4 + b
+                ref = drop(x[b].view(1, H, W, C).permute(0, 3, 1, 2), 2, s, ps, 1, 0)[0].permute(1, 2, 0)
+                assert G.rel_err(rec[b, s, ps], ref) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ convolutions
+CONV_SHAPES = [  # (NB, Cin, H, W, Cout)
+    (1, 256, 8, 16, 256),      # exactly one tile
+    (2, 256, 6, 10, 63),       # P7-like, partial tile, N=64
+    (3, 256, 12, 20, 36),      # P6-like, N=48
+    (1, 256, 24, 40, 256),     # P5-like, ragged tiles in x
+    (2, 128, 9, 17, 90),       # Cin=128, N=96, one pixel past a tile in both directions
+    (1, 64, 17, 33, 72),       # Cin=64, N=80
+    (1, 256, 16, 32, 126),     # N=128
+]
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_simt_conv_vs_fp64(shape):
+    NB, Cin, H, W, Cout = shape
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((NB, Cin, H, W), generator=g)
+    w = torch.randn((Cout, Cin, 3, 3), generator=g) * (2.0 / (9 * Cin)) ** 0.5
+    b = torch.randn((Cout,), generator=g) * 0.1
+    cpad = (Cout + 63) // 64 * 64
+    wk = ops.pack_conv_weight_f32(w.cuda(), cpad)
+    bias = torch.zeros(cpad, device="cuda")
+    bias[:Cout] = b.cuda()
+    out = ops.conv3x3_simt(ops.nchw_to_nhwc_f32(x.cuda()), wk, bias, Cout, cpad, True)
+    got = out.view(NB, H, W, Cout).permute(0, 3, 1, 2).cpu()
+    assert G.rel_err(got, G.conv_ref64(x, w, b, True)) < 1e-5
+
+
+@pytest.mark.parametrize("kblock", [32, 64])
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_tc_conv_raw_vs_fp64(shape, kblock):
+    NB, Cin, H, W, Cout = shape
+    ops.set_conv_kblock(kblock)
+    try:
+        g = torch.Generator().manual_seed(4)
+        x = torch.randn((NB, Cin, H, W), generator=g) * 2.0
+        w = torch.randn((Cout, Cin, 3, 3), generator=g) * (2.0 / (9 * Cin)) ** 0.5
+        b = torch.randn((Cout,), generator=g) * 0.1
+        got = G.tc_conv_raw(x, w, b, False)
+        ref = G.conv_ref64(x, w, b, False)
+        err = G.rel_err(got, ref)
+        cpu32 = G.rel_err(torch.nn.functional.conv2d(x, w, b, padding=1), ref)
+        print("tc conv %s kblock=%d: rel err vs fp64 %.3e (fp32 CPU conv: %.3e)" % (shape, kblock, err, cpu32))
+        assert not torch.isnan(got).any()
+        assert err < 1e-5
+    finally:
+        ops.set_conv_kblock(32)
+
+
+def test_tc_conv_hidden_dropout_and_strided_input():
+    g = torch.Generator().manual_seed(5)
+    NB, H, W = 4, 10, 18
+    x = torch.randn((NB, 256, H, W), generator=g)
+    w = torch.randn((256, 256, 3, 3), generator=g) * (2.0 / 2304) ** 0.5
+    b = torch.randn((256,), generator=g) * 0.05
+    # maps decode as image = 7 + n // (2*1), sample = n % 2, pass = 1
+    d = ops.make_dropout(0.2, 123, 7, 2, 1, 1, 0, 3, 1)
+    got = G.tc_conv_hidden(x, w, b, d)
+    ref = G.conv_ref64(x, w, b, True)
+    for n in range(NB):
+        keep = philox.dropout_keep_mask(123, 7 + n // 2, n % 2, 1, 0, 3, 1, H, W, 256, 0.2)
+        keep = torch.from_numpy(np.ascontiguousarray(keep.transpose(2, 0, 1)))
+        r = ref[n] * keep * 1.25
+        assert G.rel_err(got[n], r) < 1e-5, n
+        # dropped elements are exactly zero
+        assert float(got[n][~keep].abs().max()) == 0.0
+    # every 2nd map through in_map_stride / in_offset (how the variance heads read pass-1 maps)
+    hi, lo = ops.nchw_to_nhwc_split(x.cuda(), 16.0)
+    pcv = engine.pack_conv(w[:63], b[:63], "cuda")
+    out = torch.zeros((2, H * W, 63), device="cuda")
+    ops.conv3x3_tc(hi, lo, 16.0, 2, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, 63, 64, G.POD_OUT_RAW, False,
+                   out_f32=out, out_map_stride=H * W * 63, out_pixel_stride=63, in_map_stride=2 * H * W * 256,
+                   in_offset=H * W * 256)
+    torch.cuda.synchronize()
+    got2 = out.view(2, H, W, 63).permute(0, 3, 1, 2).cpu()
+    ref2 = G.conv_ref64(x[1::2], w[:63], b[:63], False)
+    assert G.rel_err(got2, ref2) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ scores / top-k
+def _level_off(level_hw, A=9):
+    off = [0]
+    for h, w in level_hw:
+        off.append(off[-1] + h * w * A)
+    return off
+
+
+def test_scores_and_topk_vs_oracle():
+    g = torch.Generator().manual_seed(6)
+    level_hw = [(12, 20), (6, 10), (3, 5), (2, 3), (1, 2)]
+    off = _level_off(level_hw)
+    R, K, B = off[-1], 7, 2
+    logits = torch.randn((B, R, K), generator=g) * 1.2 - 3.0
+    logvar = torch.randn((B, R, K), generator=g) * 0.5 - 2.0
+    for use_var in (True, False):
+        probs, score, cls = ops.scores(logits.cuda(), logvar.cuda() if use_var else None, off, 10, 31, 5)
+        cand_idx, cand_cnt, seg = ops.topk_levels(score, off, 100, 0.05)
+        probs, score, cls, cand_idx, cand_cnt = [t.cpu() for t in (probs, score, cls, cand_idx, cand_cnt)]
+        for b in range(B):
+            for l in range(len(level_hw)):
+                mu = logits[b, off[l]:off[l + 1]]
+                if use_var:
+                    eps = torch.from_numpy(philox.logit_normals(31, 5 + b, l, 10, mu.shape[0], K))
+                    ref = torch.mean((mu + eps * torch.sqrt(torch.exp(logvar[b, off[l]:off[l + 1]]))).sigmoid_(), 0)
+                else:
+                    ref = mu.clone().sigmoid_()
+                got = probs[b, off[l]:off[l + 1]]
+                assert torch.allclose(got, ref, rtol=1e-4, atol=1e-7)
+                # selection is checked on the GPU's own scores (bit-exact rule: top-k, stable, > thresh)
+                sc = score[b, off[l]:off[l + 1]]
+                assert torch.equal(sc, got.max(1)[0])
+                assert torch.equal(cls[b, off[l]:off[l + 1]].long(), got.max(1)[1])
+                k = min(100, sc.shape[0])
+                order = torch.sort(sc, descending=True, stable=True)[1][:k]
+                order = order[sc[order] > 0.05]
+                n = int(cand_cnt[b, l])
+                assert n == order.numel()
+                assert torch.equal(cand_idx[b, seg[l]:seg[l] + n].long(), order + off[l])
+
+
+def test_topk_ties_and_full_range():
+    # many equal scores: ties resolve to the lower anchor index; k larger than the level
+    off = [0, 5000, 5040]
+    score = torch.full((1, 5040), 0.5)
+    score[0, 100:200] = 0.75
+    score[0, 4000:4100] = 0.25
+    score[0, 5000:5040] = torch.linspace(0.01, 0.4, 40)
+    cand_idx, cand_cnt, seg = ops.topk_levels(score.cuda(), off, 1000, 0.05)
+    cand_idx, cand_cnt = cand_idx.cpu(), cand_cnt.cpu()
+    for l in range(2):
+        sc = score[0, off[l]:off[l + 1]]
+        k = min(1000, sc.shape[0])
+        order = torch.sort(sc, descending=True, stable=True)[1][:k]
+        order = order[sc[order] > 0.05]
+        assert int(cand_cnt[0, l]) == order.numel()
+        assert torch.equal(cand_idx[0, seg[l]:seg[l] + order.numel()].long(), order + off[l])
