@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec of the probabilistic-inference hot path at MC-dropout N=30 on
+1280x720 inputs (BASELINE.json configs[2]: reg_cls_var_dropout + mc_dropout_ensembles pre_nms,
+batch 32 per GPU).
+
+A step = one pass of the hot path over one batch: FPN features -> N=30 MC-dropout head loop ->
+Q1 means -> scores/top-k -> decode + aleatoric/epistemic covariance -> NMS -> rescale
+(reference src/probabilistic_inference/probabilistic_inference.py:178-407).  The ResNet-FPN backbone
+is upstream of the rebuilt path and is not part of the step.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1 under torchrun, one rank per GPU)
+  python bench.py --impl reference ...                      CPU arm: the oracle port of the same path
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+
+METRIC = "images/sec @ MC-dropout N=30, 1280x720"
+UNIT = "images/s"
+HEIGHT, WIDTH = 720, 1280
+N_MC = 30
+TOWER_FLOP_PER_LOC = 2 * 9 * 256 * 256          # 1,179,648 FLOP per location per tower conv
+
+
+def build_cfg(n_mc):
+    from pod_compare_b200.config import get_cfg
+    cfg = get_cfg()
+    cfg.MODEL.RETINANET.NUM_CLASSES = 7
+    cfg.merge_from_list([
+        "MODEL.PROBABILISTIC_MODELING.DROPOUT_RATE", 0.2,
+        "MODEL.PROBABILISTIC_MODELING.CLS_VAR_LOSS.NAME", "loss_attenuation",
+        "MODEL.PROBABILISTIC_MODELING.CLS_VAR_LOSS.NUM_SAMPLES", 10,
+        "MODEL.PROBABILISTIC_MODELING.BBOX_COV_LOSS.NAME", "negative_log_likelihood",
+        "MODEL.PROBABILISTIC_MODELING.BBOX_COV_LOSS.COVARIANCE_TYPE", "diagonal",
+        "PROBABILISTIC_INFERENCE.INFERENCE_MODE", "mc_dropout_ensembles",
+        "PROBABILISTIC_INFERENCE.AFFINITY_THRESHOLD", 0.9,
+        "PROBABILISTIC_INFERENCE.MC_DROPOUT.ENABLE", True,
+        "PROBABILISTIC_INFERENCE.MC_DROPOUT.NUM_RUNS", n_mc,
+        "PROBABILISTIC_INFERENCE.ENSEMBLES_DROPOUT.BOX_MERGE_MODE", "pre_nms"])
+    cfg.SEED = 0
+    cfg.freeze()
+    return cfg
+
+
+def workload_config(args, world):
+    return {"workload": "BASELINE configs[2]: reg_cls_var_dropout head, mc_dropout_ensembles pre_nms, N=%d, "
+                        "batch %d per GPU, 1280x720 (FPN features in, detections out)" % (args.n_mc, args.batch),
+            "global_batch": args.batch * world, "batch_per_gpu": args.batch, "mc_samples": args.n_mc,
+            "image": "%dx%d" % (WIDTH, HEIGHT), "chunk_images": args.chunk,
+            "parallelism": "image-sharded dp%d + NCCL all-gather of detections" % world,
+            "l2": "working set per step (tens of GB of activations) far exceeds the 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                     nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+            while not self._stop.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_path_rate(n_mc, samples_timed=1, threads=None, repeats=1):
+    """Times the oracle port (oracle/podref.py: the reference's algorithm in fp32 torch CPU ops) on the
+    host cores for ONE image: `samples_timed` MC samples of the head + the full post-processing, and
+    extrapolates linearly to n_mc samples (the head loop is n_mc identical iterations,
+    probabilistic_retinanet.py:104-108,517-523).  Returns (images/s, cores, description)."""
+    from oracle import podref as O
+    from pod_compare_b200 import synthetic as S
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg = build_cfg(n_mc)
+    pp = O.PathParams.from_cfg(cfg)
+    sd = S.make_head_state_dict(0, num_classes=7, use_dropout=True, cls_var=True, bbox_cov=True)
+    hw = O.unpack_head(sd, pp)
+    feats = S.make_features(0, 0, HEIGHT, WIDTH)
+    anchors = O.make_anchors([tuple(f.shape[-2:]) for f in feats], pp)
+    drop = O.DropoutSource("torch", pp.dropout_rate)
+    import torchvision          # first use pulls in seconds of lazy imports: keep them out of the timing
+    torchvision.ops.nms(torch.tensor([[0.0, 0.0, 1.0, 1.0]]), torch.tensor([1.0]), 0.5)
+    best_head, best_post = None, None
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            outs = [O.head_outputs(feats, hw, pp, drop, sample=s) for s in range(samples_timed)]
+            t_head = (time.perf_counter() - t0) / samples_timed
+            outs_n = [outs[i % samples_timed] for i in range(max(3, samples_timed))]   # epistemic branch needs >1
+            t0 = time.perf_counter()
+            cand = O.anchorwise(outs_n, anchors, pp, 0, 0, normal_mode="torch")
+            det = O.standard_nms_post(cand, pp, (HEIGHT, WIDTH))
+            O.detector_postprocess(det, HEIGHT, WIDTH)
+            t_post = time.perf_counter() - t0
+            best_head = t_head if best_head is None else min(best_head, t_head)
+            best_post = t_post if best_post is None else min(best_post, t_post)
+    per_image = n_mc * best_head + best_post
+    desc = ("1 image: %d MC sample(s) of the head timed (%.2f s each) + full post-processing (%.2f s), "
+            "extrapolated to N=%d: %.1f s/image" % (samples_timed, best_head, best_post, n_mc, per_image))
+    return 1.0 / per_image, threads, desc
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, cores, desc = cpu_path_rate(args.n_mc, samples_timed=1)
+        if i >= args.warmup:
+            vals.append(v)
+    value = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--chunk", type=int, default=16, help="images processed per head pass (memory bound)")
+    ap.add_argument("--n-mc", type=int, default=N_MC)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kblock", type=int, default=0)
+    args = ap.parse_args()
+
+    from pod_compare_b200 import distributed as D
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    D.init_from_env("nccl")
+    import torch.distributed as dist
+    from pod_compare_b200 import ops, synthetic as S
+    from pod_compare_b200.predictor import build_predictor
+    if args.kblock:
+        ops.set_conv_kblock(args.kblock)
+
+    cfg = build_cfg(args.n_mc)
+    pred = build_predictor(cfg)
+    pred.load_weight_sets(S.make_head_state_dict(0, num_classes=7, use_dropout=True, cls_var=True, bbox_cov=True))
+    B = args.batch
+    # synthetic FPN features of this rank's images (weak scaling: B images per GPU)
+    img0 = rank * B
+    host_feats = None
+    per = [S.make_features(0, img0 + i % 4, HEIGHT, WIDTH) for i in range(min(B, 4))]     # 4 distinct images, tiled
+    host_feats = [torch.cat([per[i % len(per)][l] for i in range(B)], 0).pin_memory() for l in range(5)]
+    dev_feats = [f.cuda(non_blocking=True) for f in host_feats]
+    torch.cuda.synchronize()
+    h2d_bytes = sum(f.numel() * 4 for f in host_feats)
+
+    def step(feats):
+        recs = []
+        for c0 in range(0, B, args.chunk):
+            c1 = min(B, c0 + args.chunk)
+            chunk = [f[c0:c1] for f in feats]
+            _, _, cand, det = pred.infer_from_features(chunk, (HEIGHT, WIDTH), (HEIGHT, WIDTH), image0=img0 + c0,
+                                                       return_candidates=True)
+            recs.append(D.pack_records(det))
+        rec = torch.cat(recs, 0)
+        return D.all_gather_records(rec)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    # ---- warm-up, then the device-resident measurement (value) ----
+    for _ in range(args.warmup):
+        step(dev_feats)
+    launches0 = ops.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.PROFILE = []                                  # per-launch CUDA events of the dominant kernel
+    ms, rec = timed(lambda: step(dev_feats), args.steps)
+    prof = ops.PROFILE
+    ops.PROFILE = None
+    launches = ops.launch_count() - launches0
+    # ---- end-to-end through the plugin call with HOST buffers (e2e) ----
+    d2h_bytes = rec.numel() * 4
+
+    def e2e_step():
+        r = step(host_feats)                          # infer_from_features uploads the pinned host maps
+        return r.cpu()
+
+    e2e_step()
+    ms_e2e, _ = timed(e2e_step, args.steps)
+    clocks = sampler.stop()
+
+    images = B * world * args.steps
+    value = images / (ms / 1000.0)
+    e2e_value = images / (ms_e2e / 1000.0)
+
+    # ---- roofline of the dominant kernel: the 256->256 tower convolution (tcgen05) ----
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured bf16_tflops_sustained (MEASURED_PEAKS.json)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    roof = None
+    if prof:
+        torch.cuda.synchronize()
+        tot_ms, tot_flop, n = 0.0, 0.0, 0
+        all_ms = 0.0
+        for (s, e, flop, tag) in prof:
+            d = s.elapsed_time(e)
+            all_ms += d
+            if tag == "tower256":
+                tot_ms += d
+                tot_flop += flop
+                n += 1
+        if n:
+            ach = tot_flop / (tot_ms / 1000.0) / 1e12
+            roof = {"bound": "tensor", "kernel": "k_conv3x3_tc<256,*,HIDDEN> (256->256 tower conv, fp16x3 split)",
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peak_src, "launches": n, "avg_launch_ms": tot_ms / n,
+                    "algorithmic_flop_per_launch": tot_flop / n,
+                    "mma_tflops": 3.0 * ach, "mma_frac": 3.0 * ach / peak,
+                    "conv_share_of_step": all_ms / ms,
+                    "note": "achieved counts ALGORITHMIC fp32 FLOPs (2*9*256*256 per location); each is issued as 3 fp16 "
+                            "tensor-core MMAs (hi*hi, hi*lo, lo*hi), so frac <= 1/3 by construction and mma_frac is the "
+                            "tensor-pipe utilisation"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (fp16x3 split operands on tcgen05, fp32 accumulate)", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": launches, "roofline": roof}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, desc = cpu_path_rate(args.n_mc, samples_timed=2)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

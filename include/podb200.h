@@ -193,7 +193,8 @@ int pod_decode_cov(const pod_decode_args* a, void* stream);
  * 1 bayesian_inference (mean of member vectors).
  * in : candidates from pod_decode_cov (B,cap,...) + count (B); has_cov: 0 -> zero covariances
  * out: det_* (B,max_dets,...) + det_count (B) after scale/clip/nonempty; keep (B,max_dets) = NMS
- *      survivor indices into the candidate list BEFORE the nonempty filter, keep_count (B). */
+ *      survivor indices into the candidate list BEFORE the nonempty filter, keep_count (B);
+ *      det_src (B,max_dets) = the candidate index of every final row. */
 typedef struct pod_nms_args {
   const float* boxes;
   const float* cov;
@@ -216,6 +217,7 @@ typedef struct pod_nms_args {
   int* det_count;
   int* keep;
   int* keep_count;
+  int* det_src;  /* (B,max_dets): candidate index each FINAL detection row came from */
 } pod_nms_args;
 int pod_nms_fuse(const pod_nms_args* a, void* stream);
 

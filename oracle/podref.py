@@ -304,8 +304,11 @@ class Candidates:
     level_probs: Optional[List[torch.Tensor]] = None      # per level: (HWA,K) probabilities
 
 
-def anchorwise(outputs_list, anchors, pp: PathParams, seed=0, image=0, keep_diag=False, stable_topk=True):
-    """outputs_list: list over samples/members of raw-output dicts (len 1 => no epistemic part)."""
+def anchorwise(outputs_list, anchors, pp: PathParams, seed=0, image=0, keep_diag=False, stable_topk=True,
+               normal_mode="philox"):
+    """outputs_list: list over samples/members of raw-output dicts (len 1 => no epistemic part).
+    normal_mode 'torch' draws the logit / box noise from torch's own generator, as the reference does
+    (CPU-baseline timing only; parity runs use the Philox streams)."""
     epistemic = len(outputs_list) > 1
     if epistemic:
         outputs = {"box_cls": quirk_mean([o["box_cls"] for o in outputs_list]),
@@ -325,8 +328,11 @@ def anchorwise(outputs_list, anchors, pp: PathParams, seed=0, image=0, keep_diag
         box_delta = outputs["box_delta"][i][0]
         if outputs["box_cls_var"] is not None:
             logvar = outputs["box_cls_var"][i][0]
-            eps = torch.from_numpy(philox.logit_normals(seed, image, i, pp.cls_var_num_samples,
-                                                        box_cls.shape[0], box_cls.shape[1]))
+            if normal_mode == "torch":
+                eps = torch.randn((pp.cls_var_num_samples,) + tuple(box_cls.shape))
+            else:
+                eps = torch.from_numpy(philox.logit_normals(seed, image, i, pp.cls_var_num_samples,
+                                                            box_cls.shape[0], box_cls.shape[1]))
             draws = box_cls + eps * torch.sqrt(torch.exp(logvar))       # Normal.rsample: loc + eps*scale
             box_cls = torch.mean(draws.sigmoid_(), 0)
         else:
@@ -363,7 +369,10 @@ def anchorwise(outputs_list, anchors, pp: PathParams, seed=0, image=0, keep_diag
     if isinstance(all_chol[0], torch.Tensor):
         L = torch.cat(all_chol)
         S = pp.box_num_samples
-        eps = torch.from_numpy(philox.box_normals(seed, image, ids, S))               # (S,M,4)
+        if normal_mode == "torch":
+            eps = torch.randn((S, delta.shape[0], 4))
+        else:
+            eps = torch.from_numpy(philox.box_normals(seed, image, ids, S))           # (S,M,4)
         draws = delta + torch.matmul(L, eps.unsqueeze(-1)).squeeze(-1)                  # loc + L eps
         draws = torch.transpose(torch.transpose(draws, 0, 1), 1, 2)                     # (M,4,S)
         anc_s = torch.repeat_interleave(anc.unsqueeze(2), S, dim=2)

@@ -58,7 +58,7 @@ class NmsArgs(C.Structure):
                 ("in_h", C.c_int), ("in_w", C.c_int), ("out_h", C.c_int), ("out_w", C.c_int),
                 ("det_boxes", C.c_void_p), ("det_cov", C.c_void_p), ("det_scores", C.c_void_p),
                 ("det_classes", C.c_void_p), ("det_probs", C.c_void_p), ("det_count", C.c_void_p),
-                ("keep", C.c_void_p), ("keep_count", C.c_void_p)]
+                ("keep", C.c_void_p), ("keep_count", C.c_void_p), ("det_src", C.c_void_p)]
 
 
 _lib = None

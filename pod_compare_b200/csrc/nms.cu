@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(NT) k_nms_fuse(pod_nms_args a, float sx, float
   int* det_classes = a.det_classes + (int64_t)b * a.max_dets;
   float* det_probs = a.det_probs + (int64_t)b * a.max_dets * a.K;
   int* keep_out = a.keep + (int64_t)b * a.max_dets;
+  int* src_out = a.det_src + (int64_t)b * a.max_dets;
 
   if (M <= 0) {
     if (tid == 0) { a.det_count[b] = 0; a.keep_count[b] = 0; }
@@ -397,6 +398,7 @@ __global__ void __launch_bounds__(NT) k_nms_fuse(pod_nms_args a, float sx, float
     for (int e = 0; e < 16; ++e) det_cov[p * 16 + e] = cv[e];
     det_scores[p] = pr_score;
     det_classes[p] = pr_cls;
+    src_out[p] = s_kept_idx[tid];
   }
 }
 }  // namespace
@@ -406,7 +408,7 @@ extern "C" __attribute__((visibility("default"))) int pod_nms_fuse(const pod_nms
   POD_REQUIRE(a->boxes && a->scores && a->classes && a->probs && a->count, "pod_nms_fuse: null input");
   POD_REQUIRE(a->has_cov == 0 || a->cov, "pod_nms_fuse: has_cov without cov");
   POD_REQUIRE(a->det_boxes && a->det_cov && a->det_scores && a->det_classes && a->det_probs && a->det_count && a->keep &&
-                  a->keep_count, "pod_nms_fuse: null output");
+                  a->keep_count && a->det_src, "pod_nms_fuse: null output");
   POD_REQUIRE(a->B > 0 && a->cap > 0 && a->cap <= SORT_MAX, "pod_nms_fuse: cap must be in 1..%d", SORT_MAX);
   POD_REQUIRE(a->K > 0 && a->K <= MAX_K, "pod_nms_fuse: K must be in 1..%d", MAX_K);
   POD_REQUIRE(a->max_dets > 0 && a->max_dets <= MAX_DETS, "pod_nms_fuse: max_dets must be in 1..%d", MAX_DETS);

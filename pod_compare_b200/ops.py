@@ -13,6 +13,7 @@ from . import _cabi
 from ._cabi import POD_OUT_HIDDEN, POD_OUT_RAW, ConvArgs, DecodeArgs, Dropout, NmsArgs, check, int_array, ptr, stream_ptr
 
 _launches = 0
+PROFILE = None      # bench.py sets this to a list: (start_event, end_event, algorithmic FLOPs, tag) per conv launch
 
 
 def launch_count():
@@ -153,7 +154,14 @@ def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias,
     a.out_f32 = (out_f32.data_ptr() + out_offset * 4) if out_f32 is not None else None
     a.out_map_stride, a.out_pixel_stride = out_map_stride, out_pixel_stride
     a.drop = drop if drop is not None else make_dropout()
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib.pod_conv3x3_tc(C.byref(a), stream_ptr()), "pod_conv3x3_tc")
+    if PROFILE is not None:
+        e1.record()
+        tag = "tower256" if (Cout_pad == 256 and mode == POD_OUT_HIDDEN) else ("conv1" if Cout_pad == 256 else "out")
+        PROFILE.append((e0, e1, 2.0 * 9 * Cin * Cout * NB * H * W, tag))
     _count()
 
 
@@ -288,6 +296,7 @@ def nms_fuse(cand, mode, nms_thresh, affinity, max_dets, in_hw, out_hw, nms_vari
         "count": torch.zeros((B,), dtype=torch.int32, device=dev),
         "keep": torch.zeros((B, max_dets), dtype=torch.int32, device=dev),
         "keep_count": torch.zeros((B,), dtype=torch.int32, device=dev),
+        "src": torch.zeros((B, max_dets), dtype=torch.int32, device=dev),
     }
     a = NmsArgs()
     a.boxes = _chk(cand["boxes"], torch.float32, "boxes").data_ptr()
@@ -305,6 +314,7 @@ def nms_fuse(cand, mode, nms_thresh, affinity, max_dets, in_hw, out_hw, nms_vari
     a.det_scores, a.det_classes = out["scores"].data_ptr(), out["classes"].data_ptr()
     a.det_probs, a.det_count = out["probs"].data_ptr(), out["count"].data_ptr()
     a.keep, a.keep_count = out["keep"].data_ptr(), out["keep_count"].data_ptr()
+    a.det_src = out["src"].data_ptr()
     check(lib.pod_nms_fuse(C.byref(a), stream_ptr()), "pod_nms_fuse")
     _count()
     return out
