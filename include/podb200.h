@@ -120,6 +120,10 @@ int pod_conv3x3_tc(const pod_conv_args* a, void* stream);
 /* Channels per pipeline stage of the tcgen05 kernel: 32 (SWIZZLE_64B operand tiles, deeper pipeline,
  * default) or 64 (SWIZZLE_128B).  Process-wide tuning knob; results are identical. */
 int pod_conv3x3_tc_set_kblock(int bk);
+/* 3x3 taps summed inside the tensor core before the partial sum is added in fp32 round-to-nearest by
+ * the epilogue warps: 1 (default, most accurate), 3 or 9 (single chain; tcgen05 accumulates with
+ * truncation, which drifts ~2e-5 relative over the 2304-long reduction). */
+int pod_conv3x3_tc_set_chunk_taps(int taps);
 /* Device-side error word of the last tcgen05 launch on this thread (0 = ok; set when a bounded
  * barrier wait expired).  Host pointer out. */
 int pod_conv3x3_tc_status(int* status_host);

@@ -26,7 +26,7 @@ constexpr int TILE_H = 8;
 constexpr int TILE_W = 16;
 constexpr int UMMA_K = 16;
 constexpr int ACC_COLS = 256;           // TMEM columns reserved per accumulator buffer
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;         // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
 constexpr long long WAIT_LIMIT_CYCLES = 4000000000LL;   // ~2 s: bounded waits, never hang the box
 
 __device__ int g_status = 0;            // 0 ok; else code of the barrier wait that expired
@@ -37,6 +37,7 @@ struct Params {
   int tiles_x, tiles_y, num_tiles;
   int Cout, Cout_pad;
   int relu;
+  int kb_per_chunk;     // K-blocks summed in the tensor core before an fp32 RN add in registers
   float acc_scale;      // 1 / (in_scale * w_scale)
   float out_scale;
   const float* bias;
@@ -164,6 +165,13 @@ template <int BN, int BK, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_constant__ Params P) {
   using C = Cfg<BN, BK>;
   constexpr int STAGES = C::STAGES;
+  // Accumulation is CHUNKED: the tensor core sums one chunk of the K loop (default: one 3x3 tap =
+  // Cin channels) into a fresh TMEM accumulator; the epilogue warps add the chunk results in fp32
+  // round-to-nearest in registers.  tcgen05 accumulates with truncation, so a single 2304-long chain
+  // drifts by ~2e-5 relative; per-tap chains keep the head within ~2e-6 of the fp32 reference.
+  constexpr int COLS = BN == 256 ? 128 : BN;          // accumulator columns owned by one epilogue thread
+  constexpr int EPI_THREADS = BN == 256 ? 256 : 128;  // BN=256: 8 epilogue warps (2 column halves), else 4
+  constexpr int NG = COLS / 16;
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], EPI_THREADS);
     }
     fence_barrier_init();
   }
@@ -200,144 +208,169 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
 
   const int kb_per_tap = P.Cin / BK;
   const int kb_total = 9 * kb_per_tap;
+  const int kb_per_chunk = P.kb_per_chunk;
+  const int n_chunks = kb_total / kb_per_chunk;
   const int tiles_per_map = P.tiles_x * P.tiles_y;
 
-  if (warp == 0 && lane == 0) {
-    // ================================ TMA producer ================================
-    uint32_t stage = 0, phase = 0;
-    bool ok = true;
-    for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
-      const int n = tile / tiles_per_map, r = tile % tiles_per_map;
-      const int y0 = (r / P.tiles_x) * TILE_H, x0 = (r % P.tiles_x) * TILE_W;
-      for (int tap = 0; tap < 9 && ok; ++tap) {
-        const int yy = y0 + tap / 3 - 1, xx = x0 + tap % 3 - 1;
-        for (int cb = 0; cb < kb_per_tap; ++cb) {
-          if (!mbar_wait(&empty_bar[stage], phase ^ 1u, 1)) { ok = false; break; }
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)C::STAGE_BYTES);
-          uint8_t* s = smem + (size_t)stage * C::STAGE_BYTES;
-          tma_load_4d(&P.tm_a_hi, &full_bar[stage], s, cb * BK, xx, yy, n);
-          tma_load_4d(&P.tm_a_lo, &full_bar[stage], s + C::A_BYTES, cb * BK, xx, yy, n);
-          tma_load_2d(&P.tm_b_hi, &full_bar[stage], s + 2 * C::A_BYTES, tap * P.Cin + cb * BK, 0);
-          tma_load_2d(&P.tm_b_lo, &full_bar[stage], s + 2 * C::A_BYTES + C::B_BYTES, tap * P.Cin + cb * BK, 0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+  if (warp < 4) {
+    if (warp == 0 && lane == 0) {
+      // ================================ TMA producer ================================
+      uint32_t stage = 0, phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
+        const int n = tile / tiles_per_map, r = tile % tiles_per_map;
+        const int y0 = (r / P.tiles_x) * TILE_H, x0 = (r % P.tiles_x) * TILE_W;
+        for (int tap = 0; tap < 9 && ok; ++tap) {
+          const int yy = y0 + tap / 3 - 1, xx = x0 + tap % 3 - 1;
+          for (int cb = 0; cb < kb_per_tap; ++cb) {
+            if (!mbar_wait(&empty_bar[stage], phase ^ 1u, 1)) { ok = false; break; }
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)C::STAGE_BYTES);
+            uint8_t* s = smem + (size_t)stage * C::STAGE_BYTES;
+            tma_load_4d(&P.tm_a_hi, &full_bar[stage], s, cb * BK, xx, yy, n);
+            tma_load_4d(&P.tm_a_lo, &full_bar[stage], s + C::A_BYTES, cb * BK, xx, yy, n);
+            tma_load_2d(&P.tm_b_hi, &full_bar[stage], s + 2 * C::A_BYTES, tap * P.Cin + cb * BK, 0);
+            tma_load_2d(&P.tm_b_lo, &full_bar[stage], s + 2 * C::A_BYTES + C::B_BYTES, tap * P.Cin + cb * BK, 0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
         }
       }
-    }
-  } else if (warp == 1 && lane == 0) {
-    // ================================ MMA issuer ==================================
-    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-    bool ok = true;
-    for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
-      if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 2)) break;
-      tcgen05_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-      for (int kb = 0; kb < kb_total; ++kb) {
-        if (!mbar_wait(&full_bar[stage], phase, 3)) { ok = false; break; }
-        tcgen05_fence_after();
-        const uint32_t sa_hi = smem_base + stage * C::STAGE_BYTES;
-        const uint32_t sa_lo = sa_hi + C::A_BYTES;
-        const uint32_t sb_hi = sa_hi + 2 * C::A_BYTES;
-        const uint32_t sb_lo = sb_hi + C::B_BYTES;
+    } else if (warp == 1 && lane == 0) {
+      // ================================ MMA issuer ==================================
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
+        for (int c = 0; c < n_chunks && ok; ++c) {
+          if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 2)) { ok = false; break; }
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+          for (int j = 0; j < kb_per_chunk; ++j) {
+            if (!mbar_wait(&full_bar[stage], phase, 3)) { ok = false; break; }
+            tcgen05_fence_after();
+            const uint32_t sa_hi = smem_base + stage * C::STAGE_BYTES;
+            const uint32_t sa_lo = sa_hi + C::A_BYTES;
+            const uint32_t sb_hi = sa_hi + 2 * C::A_BYTES;
+            const uint32_t sb_lo = sb_hi + C::B_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint32_t koff = k * UMMA_K * 2;
-          const uint64_t ah = make_smem_desc<C::ROW_BYTES>(sa_hi + koff);
-          const uint64_t al = make_smem_desc<C::ROW_BYTES>(sa_lo + koff);
-          const uint64_t bh = make_smem_desc<C::ROW_BYTES>(sb_hi + koff);
-          const uint64_t bl = make_smem_desc<C::ROW_BYTES>(sb_lo + koff);
-          umma_f16(d_tmem, al, bh, C::IDESC, (kb | k) != 0 ? 1u : 0u);   // small terms first
-          umma_f16(d_tmem, ah, bl, C::IDESC, 1u);
-          umma_f16(d_tmem, ah, bh, C::IDESC, 1u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint32_t koff = k * UMMA_K * 2;
+              const uint64_t ah = make_smem_desc<C::ROW_BYTES>(sa_hi + koff);
+              const uint64_t al = make_smem_desc<C::ROW_BYTES>(sa_lo + koff);
+              const uint64_t bh = make_smem_desc<C::ROW_BYTES>(sb_hi + koff);
+              const uint64_t bl = make_smem_desc<C::ROW_BYTES>(sb_lo + koff);
+              umma_f16(d_tmem, al, bh, C::IDESC, (j | k) != 0 ? 1u : 0u);   // small terms first
+              umma_f16(d_tmem, ah, bl, C::IDESC, 1u);
+              umma_f16(d_tmem, ah, bh, C::IDESC, 1u);
+            }
+            umma_commit(&empty_bar[stage]);                          // frees the smem slot when the MMAs retire
+            if (j == kb_per_chunk - 1) umma_commit(&tfull_bar[acc]);  // chunk complete -> epilogue warps
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+          acc ^= 1u;
+          if (acc == 0) acc_phase ^= 1u;
         }
-        umma_commit(&empty_bar[stage]);                    // frees the smem slot when the MMAs retire
-        if (kb == kb_total - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      acc ^= 1u;
-      if (acc == 0) acc_phase ^= 1u;
     }
-  } else if (warp >= 4) {
+  } else {
     // ================================ epilogue ====================================
-    const int ew = warp - 4;                 // == warp % 4: the TMEM lane quadrant this warp may read
-    const int m = ew * 32 + lane;            // GEMM row == TMEM lane == pixel of the tile
-    const int reps = P.drop.samples * P.drop.passes;
-    uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-      const int n = tile / tiles_per_map, r = tile % tiles_per_map;
-      const int py = (r / P.tiles_x) * TILE_H + m / TILE_W, px = (r % P.tiles_x) * TILE_W + m % TILE_W;
-      const bool valid = py < P.H && px < P.W;
-      const int pixel = py * P.W + px;
-      if (!mbar_wait(&tfull_bar[acc], acc_phase, 4)) break;
-      tcgen05_fence_after();
-      uint32_t c1 = 0, sample = 0, image = 0;
-      if (MODE == POD_OUT_HIDDEN && P.drop_thr != 0u) {
-        image = (uint32_t)(P.drop.image0 + n / reps);
-        sample = (uint32_t)((n / P.drop.passes) % P.drop.samples);
-        c1 = pod_dropout_c1(P.drop.level, P.drop.layer, P.drop.tower, P.drop.pass0 + n % P.drop.passes);
-      }
-      const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * ACC_COLS;
-#pragma unroll 1
-      for (int ch = 0; ch < BN; ch += 16) {
-        uint32_t raw[16];
-        __syncwarp();                          // tcgen05.ld is warp-collective (.sync.aligned)
-        tmem_ld16(trow + ch, raw);
-        tmem_ld_wait();
-        if (ch + 16 >= BN) {
-          // all TMEM reads of this thread are done: hand the accumulator back to the MMA warp
-          tcgen05_fence_before();
-          mbar_arrive(&tempty_bar[acc]);
-        }
-        if (valid) {
-        float v[16];
+    const int ew = warp - 4;
+    const int quad = ew & 3;                 // == warp % 4: the TMEM lane quadrant this warp may read
+    const int half = ew >> 2;                // column half (BN == 256 only)
+    if (half == 0 || BN == 256) {
+      const int m = quad * 32 + lane;        // GEMM row == TMEM lane == pixel of the tile
+      const int col0 = half * COLS;
+      const int reps = P.drop.samples * P.drop.passes;
+      uint32_t acc = 0, acc_phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
+        const int n = tile / tiles_per_map, r = tile % tiles_per_map;
+        const int py = (r / P.tiles_x) * TILE_H + m / TILE_W, px = (r % P.tiles_x) * TILE_W + m % TILE_W;
+        const bool valid = py < P.H && px < P.W;
+        const int pixel = py * P.W + px;
+        float sum[COLS];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          v[i] = fmaf(__uint_as_float(raw[i]), P.acc_scale, __ldg(P.bias + ch + i));
-          if (P.relu) v[i] = fmaxf(v[i], 0.f);
-        }
-        if (MODE == POD_OUT_HIDDEN) {
-          if (P.drop_thr != 0u) {
+        for (int i = 0; i < COLS; ++i) sum[i] = 0.f;
+        for (int c = 0; c < n_chunks; ++c) {
+          if (!mbar_wait(&tfull_bar[acc], acc_phase, 4)) { ok = false; break; }
+          tcgen05_fence_after();
+          const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_COLS + col0;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t q = (uint32_t)(((long long)pixel * P.Cout_pad + ch + g * 4) >> 2);
-              const uint4 w = philox4x32_10(q, c1, sample, image, P.key);
-              v[g * 4 + 0] = w.x >= P.drop_thr ? v[g * 4 + 0] * P.drop_scale : 0.f;
-              v[g * 4 + 1] = w.y >= P.drop_thr ? v[g * 4 + 1] * P.drop_scale : 0.f;
-              v[g * 4 + 2] = w.z >= P.drop_thr ? v[g * 4 + 2] * P.drop_scale : 0.f;
-              v[g * 4 + 3] = w.w >= P.drop_thr ? v[g * 4 + 3] * P.drop_scale : 0.f;
+          for (int g = 0; g < NG; g += 2) {
+            uint32_t r0[16], r1[16];
+            __syncwarp();                          // tcgen05.ld is warp-collective (.sync.aligned)
+            tmem_ld16(trow + g * 16, r0);
+            if (g + 1 < NG) tmem_ld16(trow + (g + 1) * 16, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sum[g * 16 + i] = __fadd_rn(sum[g * 16 + i], __uint_as_float(r0[i]));
+            if (g + 1 < NG) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sum[(g + 1) * 16 + i] = __fadd_rn(sum[(g + 1) * 16 + i], __uint_as_float(r1[i]));
             }
           }
-          uint32_t ph[8], pl[8];
+          // all TMEM reads of this chunk are done: hand the accumulator back to the MMA warp
+          tcgen05_fence_before();
+          mbar_arrive(&tempty_bar[acc]);
+          acc ^= 1u;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+        if (!ok || !valid) continue;
+        uint32_t c1 = 0, sample = 0, image = 0;
+        if (MODE == POD_OUT_HIDDEN && P.drop_thr != 0u) {
+          image = (uint32_t)(P.drop.image0 + n / reps);
+          sample = (uint32_t)((n / P.drop.passes) % P.drop.samples);
+          c1 = pod_dropout_c1(P.drop.level, P.drop.layer, P.drop.tower, P.drop.pass0 + n % P.drop.passes);
+        }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            __half h0, l0, h1, l1;
-            pod_split_h(v[2 * i] * P.out_scale, h0, l0);
-            pod_split_h(v[2 * i + 1] * P.out_scale, h1, l1);
-            ph[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            pl[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        for (int g = 0; g < NG; ++g) {
+          const int ch = col0 + g * 16;
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] = fmaf(sum[g * 16 + i], P.acc_scale, __ldg(P.bias + ch + i));
+            if (P.relu) v[i] = fmaxf(v[i], 0.f);
           }
-          const long long o = ((long long)n * P.H * P.W + pixel) * P.Cout_pad + ch;
-          uint4* dh = reinterpret_cast<uint4*>(P.out_hi + o);
-          uint4* dl = reinterpret_cast<uint4*>(P.out_lo + o);
-          dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-          dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
-          dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-          dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
-        } else {
-          float* o = P.out_f32 + (long long)n * P.out_map_stride + (long long)pixel * P.out_pixel_stride + ch;
-          if (ch + 16 <= P.Cout && ((P.out_map_stride | P.out_pixel_stride) & 3) == 0) {
-            float4* o4 = reinterpret_cast<float4*>(o);
+          if (MODE == POD_OUT_HIDDEN) {
+            if (P.drop_thr != 0u) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) o4[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const uint32_t q = (uint32_t)(((long long)pixel * P.Cout_pad + ch + q4 * 4) >> 2);
+                const uint4 w = philox4x32_10(q, c1, sample, image, P.key);
+                v[q4 * 4 + 0] = w.x >= P.drop_thr ? v[q4 * 4 + 0] * P.drop_scale : 0.f;
+                v[q4 * 4 + 1] = w.y >= P.drop_thr ? v[q4 * 4 + 1] * P.drop_scale : 0.f;
+                v[q4 * 4 + 2] = w.z >= P.drop_thr ? v[q4 * 4 + 2] * P.drop_scale : 0.f;
+                v[q4 * 4 + 3] = w.w >= P.drop_thr ? v[q4 * 4 + 3] * P.drop_scale : 0.f;
+              }
+            }
+            uint32_t ph[8], pl[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __half h0, l0, h1, l1;
+              pod_split_h(v[2 * i] * P.out_scale, h0, l0);
+              pod_split_h(v[2 * i + 1] * P.out_scale, h1, l1);
+              ph[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+              pl[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            }
+            const long long o = ((long long)n * P.H * P.W + pixel) * P.Cout_pad + ch;
+            uint4* dh = reinterpret_cast<uint4*>(P.out_hi + o);
+            uint4* dl = reinterpret_cast<uint4*>(P.out_lo + o);
+            dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+            dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
           } else {
+            float* o = P.out_f32 + (long long)n * P.out_map_stride + (long long)pixel * P.out_pixel_stride + ch;
+            if (ch + 16 <= P.Cout && ((P.out_map_stride | P.out_pixel_stride) & 3) == 0) {
+              float4* o4 = reinterpret_cast<float4*>(o);
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (ch + i < P.Cout) o[i] = v[i];
+              for (int q4 = 0; q4 < 4; ++q4) o4[q4] = make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (ch + i < P.Cout) o[i] = v[i];
+            }
           }
         }
-        }  // valid
       }
-      acc ^= 1u;
-      if (acc == 0) acc_phase ^= 1u;
     }
   }
 
@@ -426,7 +459,14 @@ static int dispatch_bn(const Params& P, cudaStream_t st) {
 
 }  // namespace tc
 
-static int g_tc_bk = 32;   // K-block (channels per pipeline stage): 32 -> SWIZZLE_64B, 64 -> SWIZZLE_128B
+static int g_tc_bk = 32;      // K-block (channels per pipeline stage): 32 -> SWIZZLE_64B, 64 -> SWIZZLE_128B
+static int g_tc_taps = 1;     // taps per accumulation chunk (1, 3 or 9)
+
+extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_chunk_taps(int taps) {
+  POD_REQUIRE(taps == 1 || taps == 3 || taps == 9, "pod_conv3x3_tc_set_chunk_taps: 1, 3 or 9");
+  g_tc_taps = taps;
+  return 0;
+}
 
 extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_kblock(int bk) {
   POD_REQUIRE(bk == 32 || bk == 64, "pod_conv3x3_tc_set_kblock: 32 or 64");
@@ -461,6 +501,7 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   P.num_tiles = (int)nt;
   P.Cout = a->Cout; P.Cout_pad = a->Cout_pad;
   P.relu = a->relu;
+  P.kb_per_chunk = g_tc_taps * (a->Cin / BK);
   P.acc_scale = 1.0f / (a->in_scale * a->w_scale);
   P.out_scale = a->out_scale;
   P.bias = a->bias;

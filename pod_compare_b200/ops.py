@@ -176,6 +176,10 @@ def set_conv_kblock(bk):
     check(_cabi.load_library().pod_conv3x3_tc_set_kblock(int(bk)), "pod_conv3x3_tc_set_kblock")
 
 
+def set_conv_chunk_taps(taps):
+    check(_cabi.load_library().pod_conv3x3_tc_set_chunk_taps(int(taps)), "pod_conv3x3_tc_set_chunk_taps")
+
+
 def conv3x3_simt(x, w_kc, bias, Cout, Cout_pad, relu, drop=None, out=None, out_map_stride=None, out_pixel_stride=None,
                  out_offset=0):
     lib = _cabi.require_device()

@@ -131,6 +131,26 @@ def test_tc_conv_raw_vs_fp64(shape, kblock):
         ops.set_conv_kblock(32)
 
 
+def test_tc_conv_chunked_accumulation_is_more_accurate():
+    """tcgen05 accumulates with truncation; summing one tap per TMEM chain and adding the nine partial
+    sums in fp32 RN (the default) must beat the single 2304-long chain and stay within 3e-6."""
+    g = torch.Generator().manual_seed(8)
+    x = torch.relu(torch.randn((1, 256, 24, 40), generator=g)) * 1.25
+    w = torch.randn((256, 256, 3, 3), generator=g) * (2.0 / 2304) ** 0.5
+    b = torch.randn((256,), generator=g) * 0.05
+    ref = G.conv_ref64(x, w, b, False)
+    err = {}
+    try:
+        for taps in (9, 1):
+            ops.set_conv_chunk_taps(taps)
+            err[taps] = G.rel_err(G.tc_conv_raw(x, w, b, False), ref)
+    finally:
+        ops.set_conv_chunk_taps(1)
+    print("conv rel err vs fp64: single chain %.3e, per-tap chunks %.3e" % (err[9], err[1]))
+    assert err[1] < 3e-6
+    assert err[1] < err[9]
+
+
 def test_tc_conv_hidden_dropout_and_strided_input():
     g = torch.Generator().manual_seed(5)
     NB, H, W = 4, 10, 18
