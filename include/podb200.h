@@ -124,6 +124,8 @@ int pod_conv3x3_tc_set_kblock(int bk);
  * the epilogue warps: 1 (default, most accurate), 3 or 9 (single chain; tcgen05 accumulates with
  * truncation, which drifts ~2e-5 relative over the 2304-long reduction). */
 int pod_conv3x3_tc_set_chunk_taps(int taps);
+/* 256-output-channel convolutions on CTA pairs (tcgen05 cta_group::2, default on) or on single CTAs. */
+int pod_conv3x3_tc_set_pair(int on);
 /* Device-side error word of the last tcgen05 launch on this thread (0 = ok; set when a bounded
  * barrier wait expired).  Host pointer out. */
 int pod_conv3x3_tc_status(int* status_host);

@@ -161,6 +161,68 @@ struct Cfg {
   static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
 
+// bias / ReLU / Philox dropout / store of one pixel row: NG groups of 16 accumulator columns from `sum`
+template <int MODE, int NG>
+__device__ __forceinline__ void tile_epilogue(const Params& P, const float (&sum)[NG * 16], int n, int pixel, int col0) {
+    const int reps = P.drop.samples * P.drop.passes;
+    uint32_t c1 = 0, sample = 0, image = 0;
+    if (MODE == POD_OUT_HIDDEN && P.drop_thr != 0u) {
+      image = (uint32_t)(P.drop.image0 + n / reps);
+      sample = (uint32_t)((n / P.drop.passes) % P.drop.samples);
+      c1 = pod_dropout_c1(P.drop.level, P.drop.layer, P.drop.tower, P.drop.pass0 + n % P.drop.passes);
+    }
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const int ch = col0 + g * 16;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        v[i] = fmaf(sum[g * 16 + i], P.acc_scale, __ldg(P.bias + ch + i));
+        if (P.relu) v[i] = fmaxf(v[i], 0.f);
+      }
+      if (MODE == POD_OUT_HIDDEN) {
+        if (P.drop_thr != 0u) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const uint32_t q = (uint32_t)(((long long)pixel * P.Cout_pad + ch + q4 * 4) >> 2);
+            const uint4 w = philox4x32_10(q, c1, sample, image, P.key);
+            v[q4 * 4 + 0] = w.x >= P.drop_thr ? v[q4 * 4 + 0] * P.drop_scale : 0.f;
+            v[q4 * 4 + 1] = w.y >= P.drop_thr ? v[q4 * 4 + 1] * P.drop_scale : 0.f;
+            v[q4 * 4 + 2] = w.z >= P.drop_thr ? v[q4 * 4 + 2] * P.drop_scale : 0.f;
+            v[q4 * 4 + 3] = w.w >= P.drop_thr ? v[q4 * 4 + 3] * P.drop_scale : 0.f;
+          }
+        }
+        uint32_t ph[8], pl[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          __half h0, l0, h1, l1;
+          pod_split_h(v[2 * i] * P.out_scale, h0, l0);
+          pod_split_h(v[2 * i + 1] * P.out_scale, h1, l1);
+          ph[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          pl[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
+        const long long o = ((long long)n * P.H * P.W + pixel) * P.Cout_pad + ch;
+        uint4* dh = reinterpret_cast<uint4*>(P.out_hi + o);
+        uint4* dl = reinterpret_cast<uint4*>(P.out_lo + o);
+        dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+        dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+      } else {
+        float* o = P.out_f32 + (long long)n * P.out_map_stride + (long long)pixel * P.out_pixel_stride + ch;
+        if (ch + 16 <= P.Cout && ((P.out_map_stride | P.out_pixel_stride) & 3) == 0) {
+          float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) o4[q4] = make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (ch + i < P.Cout) o[i] = v[i];
+        }
+      }
+    }
+}
+
 template <int BN, int BK, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_constant__ Params P) {
   using C = Cfg<BN, BK>;
@@ -278,7 +340,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
     if (half == 0 || BN == 256) {
       const int m = quad * 32 + lane;        // GEMM row == TMEM lane == pixel of the tile
       const int col0 = half * COLS;
-      const int reps = P.drop.samples * P.drop.passes;
       uint32_t acc = 0, acc_phase = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
@@ -314,62 +375,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
           if (acc == 0) acc_phase ^= 1u;
         }
         if (!ok || !valid) continue;
-        uint32_t c1 = 0, sample = 0, image = 0;
-        if (MODE == POD_OUT_HIDDEN && P.drop_thr != 0u) {
-          image = (uint32_t)(P.drop.image0 + n / reps);
-          sample = (uint32_t)((n / P.drop.passes) % P.drop.samples);
-          c1 = pod_dropout_c1(P.drop.level, P.drop.layer, P.drop.tower, P.drop.pass0 + n % P.drop.passes);
-        }
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          const int ch = col0 + g * 16;
-          float v[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[i] = fmaf(sum[g * 16 + i], P.acc_scale, __ldg(P.bias + ch + i));
-            if (P.relu) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (MODE == POD_OUT_HIDDEN) {
-            if (P.drop_thr != 0u) {
-#pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) {
-                const uint32_t q = (uint32_t)(((long long)pixel * P.Cout_pad + ch + q4 * 4) >> 2);
-                const uint4 w = philox4x32_10(q, c1, sample, image, P.key);
-                v[q4 * 4 + 0] = w.x >= P.drop_thr ? v[q4 * 4 + 0] * P.drop_scale : 0.f;
-                v[q4 * 4 + 1] = w.y >= P.drop_thr ? v[q4 * 4 + 1] * P.drop_scale : 0.f;
-                v[q4 * 4 + 2] = w.z >= P.drop_thr ? v[q4 * 4 + 2] * P.drop_scale : 0.f;
-                v[q4 * 4 + 3] = w.w >= P.drop_thr ? v[q4 * 4 + 3] * P.drop_scale : 0.f;
-              }
-            }
-            uint32_t ph[8], pl[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              __half h0, l0, h1, l1;
-              pod_split_h(v[2 * i] * P.out_scale, h0, l0);
-              pod_split_h(v[2 * i + 1] * P.out_scale, h1, l1);
-              ph[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-              pl[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-            }
-            const long long o = ((long long)n * P.H * P.W + pixel) * P.Cout_pad + ch;
-            uint4* dh = reinterpret_cast<uint4*>(P.out_hi + o);
-            uint4* dl = reinterpret_cast<uint4*>(P.out_lo + o);
-            dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-            dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
-            dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-            dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
-          } else {
-            float* o = P.out_f32 + (long long)n * P.out_map_stride + (long long)pixel * P.out_pixel_stride + ch;
-            if (ch + 16 <= P.Cout && ((P.out_map_stride | P.out_pixel_stride) & 3) == 0) {
-              float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) o4[q4] = make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (ch + i < P.Cout) o[i] = v[i];
-            }
-          }
-        }
+        tile_epilogue<MODE, NG>(P, sum, n, pixel, col0);
       }
     }
   }
@@ -379,6 +385,251 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =====================================================================================================
+// cta_group::2 variant for the 256->256 convolutions: a cluster of two CTAs (one SM pair) computes two
+// adjacent 128-pixel tiles against ONE copy of the weight K-block -- each CTA stages its own activation
+// tile and HALF of the weight rows, the leader CTA issues tcgen05.mma.cta_group::2 (M=256, N=256) which
+// reads both halves, and each CTA's TMEM receives its own 128 accumulator rows.  Compared with the
+// single-CTA kernel this halves the weight traffic into each SM and the shared-memory operand reads
+// per MMA, which is what bounds the 1-CTA kernel.
+// =====================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t nclusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(const CUtensorMap* tm, uint32_t mbar_cluster_addr, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(const CUtensorMap* tm, uint32_t mbar_cluster_addr, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once the issued MMAs retire) on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+template <int BK>
+struct Cfg2 {
+  static constexpr int ROW_BYTES = BK * 2;
+  static constexpr int A_BYTES = BM * ROW_BYTES;            // this CTA's 128 pixel rows
+  static constexpr int B_BYTES = 128 * ROW_BYTES;           // this CTA's half of the 256 weight rows
+  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+  // D=f32, A=B=f16, K-major, N=256, M=256 (pair)
+  static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+};
+
+template <int BK, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc2(const __grid_constant__ Params P) {
+  using C = Cfg2<BK>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int COLS = 128, NG = 8, EPI_THREADS = 256;
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];    // used in the leader CTA only
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];       // used in the leader CTA only
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  uint8_t* smem = smem_dyn + (smem_base - smem_u32(smem_dyn));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.tm_a_hi);
+    tma_prefetch_desc(&P.tm_a_lo);
+    tma_prefetch_desc(&P.tm_b_hi);
+    tma_prefetch_desc(&P.tm_b_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * EPI_THREADS);       // epilogue threads of BOTH CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc2(&tmem_base_s, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                   // peer barriers initialised, both TMEM halves allocated
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int kb_per_tap = P.Cin / BK;
+  const int kb_total = 9 * kb_per_tap;
+  const int kb_per_chunk = P.kb_per_chunk;
+  const int n_chunks = kb_total / kb_per_chunk;
+  const int tiles_per_map = P.tiles_x * P.tiles_y;
+  const int num_pairs = (P.num_tiles + 1) >> 1;
+  const int pair0 = (int)cluster_id_x(), pair_step = (int)nclusters_x();
+
+  if (warp == 0 && lane == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    uint32_t stage = 0, phase = 0;
+    bool ok = true;
+    for (int tp = pair0; tp < num_pairs && ok; tp += pair_step) {
+      const int tile = 2 * tp + (int)rank;
+      // the odd tail tile of the last pair loads map index NB: entirely out of bounds -> zero fill
+      const int n = tile < P.num_tiles ? tile / tiles_per_map : P.NB;
+      const int r = tile < P.num_tiles ? tile % tiles_per_map : 0;
+      const int y0 = (r / P.tiles_x) * TILE_H, x0 = (r % P.tiles_x) * TILE_W;
+      for (int tap = 0; tap < 9 && ok; ++tap) {
+        const int yy = y0 + tap / 3 - 1, xx = x0 + tap % 3 - 1;
+        for (int cb = 0; cb < kb_per_tap; ++cb) {
+          if (!mbar_wait(&empty_bar[stage], phase ^ 1u, 11)) { ok = false; break; }
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)C::STAGE_BYTES);
+          const uint32_t fb = mapa_cluster(smem_u32(&full_bar[stage]), 0);   // the leader's full barrier
+          uint8_t* s = smem + (size_t)stage * C::STAGE_BYTES;
+          tma2_load_4d(&P.tm_a_hi, fb, s, cb * BK, xx, yy, n);
+          tma2_load_4d(&P.tm_a_lo, fb, s + C::A_BYTES, cb * BK, xx, yy, n);
+          tma2_load_2d(&P.tm_b_hi, fb, s + 2 * C::A_BYTES, tap * P.Cin + cb * BK, (int)rank * 128);
+          tma2_load_2d(&P.tm_b_lo, fb, s + 2 * C::A_BYTES + C::B_BYTES, tap * P.Cin + cb * BK, (int)rank * 128);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ================================ MMA issuer (leader CTA) =================================
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    bool ok = true;
+    for (int tp = pair0; tp < num_pairs && ok; tp += pair_step) {
+      for (int c = 0; c < n_chunks && ok; ++c) {
+        if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 12)) { ok = false; break; }
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        for (int j = 0; j < kb_per_chunk; ++j) {
+          if (!mbar_wait(&full_bar[stage], phase, 13)) { ok = false; break; }
+          tcgen05_fence_after();
+          const uint32_t sa_hi = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sa_lo = sa_hi + C::A_BYTES;
+          const uint32_t sb_hi = sa_hi + 2 * C::A_BYTES;
+          const uint32_t sb_lo = sb_hi + C::B_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint32_t koff = k * UMMA_K * 2;
+            const uint64_t ah = make_smem_desc<C::ROW_BYTES>(sa_hi + koff);
+            const uint64_t al = make_smem_desc<C::ROW_BYTES>(sa_lo + koff);
+            const uint64_t bh = make_smem_desc<C::ROW_BYTES>(sb_hi + koff);
+            const uint64_t bl = make_smem_desc<C::ROW_BYTES>(sb_lo + koff);
+            umma2_f16(d_tmem, al, bh, C::IDESC, (j | k) != 0 ? 1u : 0u);
+            umma2_f16(d_tmem, ah, bl, C::IDESC, 1u);
+            umma2_f16(d_tmem, ah, bh, C::IDESC, 1u);
+          }
+          umma2_commit_mc(&empty_bar[stage]);                          // frees the slot in both CTAs
+          if (j == kb_per_chunk - 1) umma2_commit_mc(&tfull_bar[acc]);  // chunk complete in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue (both CTAs) ====================================
+    const int ew = warp - 4;
+    const int quad = ew & 3, half = ew >> 2;
+    const int m = quad * 32 + lane;
+    const int col0 = half * COLS;
+    uint32_t acc = 0, acc_phase = 0;
+    bool ok = true;
+    const uint32_t te0 = mapa_cluster(smem_u32(&tempty_bar[0]), 0), te1 = mapa_cluster(smem_u32(&tempty_bar[1]), 0);
+    for (int tp = pair0; tp < num_pairs && ok; tp += pair_step) {
+      const int tile = 2 * tp + (int)rank;
+      const bool tile_ok = tile < P.num_tiles;
+      const int n = tile_ok ? tile / tiles_per_map : 0, r = tile_ok ? tile % tiles_per_map : 0;
+      const int py = (r / P.tiles_x) * TILE_H + m / TILE_W, px = (r % P.tiles_x) * TILE_W + m % TILE_W;
+      const bool valid = tile_ok && py < P.H && px < P.W;
+      const int pixel = py * P.W + px;
+      float sum[COLS];
+#pragma unroll
+      for (int i = 0; i < COLS; ++i) sum[i] = 0.f;
+      for (int c = 0; c < n_chunks; ++c) {
+        if (!mbar_wait(&tfull_bar[acc], acc_phase, 14)) { ok = false; break; }
+        tcgen05_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_COLS + col0;
+#pragma unroll
+        for (int g = 0; g < NG; g += 2) {
+          uint32_t r0[16], r1[16];
+          __syncwarp();
+          tmem_ld16(trow + g * 16, r0);
+          tmem_ld16(trow + (g + 1) * 16, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sum[g * 16 + i] = __fadd_rn(sum[g * 16 + i], __uint_as_float(r0[i]));
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sum[(g + 1) * 16 + i] = __fadd_rn(sum[(g + 1) * 16 + i], __uint_as_float(r1[i]));
+        }
+        tcgen05_fence_before();
+        mbar_arrive_cluster(acc ? te1 : te0);            // the leader's MMA thread tracks both CTAs
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      if (!ok || !valid) continue;
+      tile_epilogue<MODE, NG>(P, sum, n, pixel, col0);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                   // nobody exits while the peer may still signal it
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc2(tmem_base, 512);
   }
 }
 
@@ -443,7 +694,27 @@ static int launch(const Params& P, cudaStream_t st) {
 }
 
 template <int BK, int MODE>
+static int launch2(const Params& P, cudaStream_t st) {
+  using C = Cfg2<BK>;
+  auto kern = k_conv3x3_tc2<BK, MODE>;
+  static bool configured = false;
+  if (!configured) {
+    POD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  const int pairs = (P.num_tiles + 1) / 2;
+  const int max_pairs = pod_num_sms() / 2;
+  const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(P);
+  POD_LAUNCH_CHECK();
+  return 0;
+}
+
+static int g_tc_pair = 1;   // 1: 256-channel convs run on CTA pairs (cta_group::2); 0: single-CTA kernel
+
+template <int BK, int MODE>
 static int dispatch_bn(const Params& P, cudaStream_t st) {
+  if (P.Cout_pad == 256 && g_tc_pair) return launch2<BK, MODE>(P, st);
   switch (P.Cout_pad) {
     case 256: return launch<256, BK, MODE>(P, st);
     case 128: return launch<128, BK, MODE>(P, st);
@@ -461,6 +732,11 @@ static int dispatch_bn(const Params& P, cudaStream_t st) {
 
 static int g_tc_bk = 32;      // K-block (channels per pipeline stage): 32 -> SWIZZLE_64B, 64 -> SWIZZLE_128B
 static int g_tc_taps = 1;     // taps per accumulation chunk (1, 3 or 9)
+
+extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_pair(int on) {
+  tc::g_tc_pair = on ? 1 : 0;
+  return 0;
+}
 
 extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_chunk_taps(int taps) {
   POD_REQUIRE(taps == 1 || taps == 3 || taps == 9, "pod_conv3x3_tc_set_chunk_taps: 1, 3 or 9");
@@ -491,8 +767,10 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   int rc;
   if ((rc = encode_act(&P.tm_a_hi, a->in_hi, a->Cin, a->W, a->H, a->NB, a->in_map_stride, BK))) return rc;
   if ((rc = encode_act(&P.tm_a_lo, a->in_lo, a->Cin, a->W, a->H, a->NB, a->in_map_stride, BK))) return rc;
-  if ((rc = encode_wt(&P.tm_b_hi, a->w_hi, 9 * a->Cin, a->Cout_pad, BK, a->Cout_pad))) return rc;
-  if ((rc = encode_wt(&P.tm_b_lo, a->w_lo, 9 * a->Cin, a->Cout_pad, BK, a->Cout_pad))) return rc;
+  // CTA pairs stage half of the 256 weight rows each
+  const int b_box_rows = (a->Cout_pad == 256 && tc::g_tc_pair) ? 128 : a->Cout_pad;
+  if ((rc = encode_wt(&P.tm_b_hi, a->w_hi, 9 * a->Cin, a->Cout_pad, BK, b_box_rows))) return rc;
+  if ((rc = encode_wt(&P.tm_b_lo, a->w_lo, 9 * a->Cin, a->Cout_pad, BK, b_box_rows))) return rc;
   P.NB = a->NB; P.H = a->H; P.W = a->W; P.Cin = a->Cin;
   P.tiles_x = (a->W + TILE_W - 1) / TILE_W;
   P.tiles_y = (a->H + TILE_H - 1) / TILE_H;

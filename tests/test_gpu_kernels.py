@@ -84,7 +84,9 @@ def test_mask_expand_matches_oracle():
 
 # ------------------------------------------------------------------------------------------ convolutions
 CONV_SHAPES = [  # (NB, Cin, H, W, Cout)
-    (1, 256, 8, 16, 256),      # exactly one tile
+    (1, 256, 8, 16, 256),      # exactly one tile (odd tile count: the pair kernel's tail path)
+    (3, 256, 20, 40, 256),     # 27 tiles per launch, ragged in x and y, odd count
+    (5, 64, 8, 32, 256),       # 10 tiles, Cin=64
     (2, 256, 6, 10, 63),       # P7-like, partial tile, N=64
     (3, 256, 12, 20, 36),      # P6-like, N=48
     (1, 256, 24, 40, 256),     # P5-like, ragged tiles in x
@@ -110,11 +112,15 @@ def test_simt_conv_vs_fp64(shape):
     assert G.rel_err(got, G.conv_ref64(x, w, b, True)) < 1e-5
 
 
+@pytest.mark.parametrize("pair", [1, 0])
 @pytest.mark.parametrize("kblock", [32, 64])
 @pytest.mark.parametrize("shape", CONV_SHAPES)
-def test_tc_conv_raw_vs_fp64(shape, kblock):
+def test_tc_conv_raw_vs_fp64(shape, kblock, pair):
     NB, Cin, H, W, Cout = shape
+    if pair == 0 and Cout != 256:
+        pytest.skip("single-CTA / paired choice only exists for 256 output channels")
     ops.set_conv_kblock(kblock)
+    ops.set_conv_pair(pair)
     try:
         g = torch.Generator().manual_seed(4)
         x = torch.randn((NB, Cin, H, W), generator=g) * 2.0
@@ -129,6 +135,7 @@ def test_tc_conv_raw_vs_fp64(shape, kblock):
         assert err < 1e-5
     finally:
         ops.set_conv_kblock(32)
+        ops.set_conv_pair(1)
 
 
 def test_tc_conv_chunked_accumulation_is_more_accurate():
