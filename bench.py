@@ -167,6 +167,8 @@ def main():
     ap.add_argument("--n-mc", type=int, default=N_MC)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kblock", type=int, default=0)
+    ap.add_argument("--pair", type=int, default=-1, help="1/0: force CTA-pair (cta_group::2) / single-CTA tower convs")
+    ap.add_argument("--chunk-taps", type=int, default=0, help="taps per accumulation chunk (1, 3, 9)")
     args = ap.parse_args()
 
     from pod_compare_b200 import distributed as D
@@ -184,6 +186,10 @@ def main():
     from pod_compare_b200.predictor import build_predictor
     if args.kblock:
         ops.set_conv_kblock(args.kblock)
+    if args.pair >= 0:
+        ops.set_conv_pair(args.pair)
+    if args.chunk_taps:
+        ops.set_conv_chunk_taps(args.chunk_taps)
 
     cfg = build_cfg(args.n_mc)
     pred = build_predictor(cfg)

@@ -162,15 +162,34 @@ struct Cfg {
 };
 
 // bias / ReLU / Philox dropout / store of one pixel row: NG groups of 16 accumulator columns from `sum`
-template <int MODE, int NG>
-__device__ __forceinline__ void tile_epilogue(const Params& P, const float (&sum)[NG * 16], int n, int pixel, int col0) {
-    const int reps = P.drop.samples * P.drop.passes;
-    uint32_t c1 = 0, sample = 0, image = 0;
-    if (MODE == POD_OUT_HIDDEN && P.drop_thr != 0u) {
-      image = (uint32_t)(P.drop.image0 + n / reps);
-      sample = (uint32_t)((n / P.drop.passes) % P.drop.samples);
-      c1 = pod_dropout_c1(P.drop.level, P.drop.layer, P.drop.tower, P.drop.pass0 + n % P.drop.passes);
+// Dropout keep-bits of one pixel row: bit j of keep[] <-> accumulator column col0 + j.  The Philox calls
+// are independent of the accumulators, so the epilogue warps evaluate them in slices while they wait for
+// the next accumulation chunk (`slice` of `n_slices`); only a cheap select remains for the tile end.
+template <int NG>
+__device__ __forceinline__ void dropout_bits_slice(const Params& P, int n, int pixel, int col0, int slice, int n_slices,
+                                                   uint32_t (&keep)[(NG * 16 + 31) / 32]) {
+  constexpr int CALLS = NG * 4;
+  const int per = (CALLS + n_slices - 1) / n_slices;
+  const int reps = P.drop.samples * P.drop.passes;
+  const uint32_t image = (uint32_t)(P.drop.image0 + n / reps);
+  const uint32_t sample = (uint32_t)((n / P.drop.passes) % P.drop.samples);
+  const uint32_t c1 = pod_dropout_c1(P.drop.level, P.drop.layer, P.drop.tower, P.drop.pass0 + n % P.drop.passes);
+#pragma unroll
+  for (int q = 0; q < CALLS; ++q) {
+    if (q / per == slice) {
+      const uint32_t ctr = (uint32_t)(((long long)pixel * P.Cout_pad + col0 + q * 4) >> 2);
+      const uint4 w = philox4x32_10(ctr, c1, sample, image, P.key);
+      const uint32_t b = (w.x >= P.drop_thr ? 1u : 0u) | (w.y >= P.drop_thr ? 2u : 0u) | (w.z >= P.drop_thr ? 4u : 0u) |
+                         (w.w >= P.drop_thr ? 8u : 0u);
+      keep[q / 8] |= b << ((q % 8) * 4);
     }
+  }
+}
+
+// bias / ReLU / dropout select / store of one pixel row: NG groups of 16 accumulator columns from `sum`
+template <int MODE, int NG>
+__device__ __forceinline__ void tile_epilogue(const Params& P, const float (&sum)[NG * 16], int n, int pixel, int col0,
+                                              const uint32_t (&keep)[(NG * 16 + 31) / 32]) {
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       const int ch = col0 + g * 16;
@@ -182,15 +201,9 @@ __device__ __forceinline__ void tile_epilogue(const Params& P, const float (&sum
       }
       if (MODE == POD_OUT_HIDDEN) {
         if (P.drop_thr != 0u) {
+          const uint32_t bits = keep[g / 2] >> ((g % 2) * 16);
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const uint32_t q = (uint32_t)(((long long)pixel * P.Cout_pad + ch + q4 * 4) >> 2);
-            const uint4 w = philox4x32_10(q, c1, sample, image, P.key);
-            v[q4 * 4 + 0] = w.x >= P.drop_thr ? v[q4 * 4 + 0] * P.drop_scale : 0.f;
-            v[q4 * 4 + 1] = w.y >= P.drop_thr ? v[q4 * 4 + 1] * P.drop_scale : 0.f;
-            v[q4 * 4 + 2] = w.z >= P.drop_thr ? v[q4 * 4 + 2] * P.drop_scale : 0.f;
-            v[q4 * 4 + 3] = w.w >= P.drop_thr ? v[q4 * 4 + 3] * P.drop_scale : 0.f;
-          }
+          for (int i = 0; i < 16; ++i) v[i] = ((bits >> i) & 1u) ? v[i] * P.drop_scale : 0.f;
         }
         uint32_t ph[8], pl[8];
 #pragma unroll
@@ -348,8 +361,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
         const bool valid = py < P.H && px < P.W;
         const int pixel = py * P.W + px;
         float sum[COLS];
+        uint32_t keep[(COLS + 31) / 32];
 #pragma unroll
         for (int i = 0; i < COLS; ++i) sum[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < (COLS + 31) / 32; ++i) keep[i] = 0u;
         for (int c = 0; c < n_chunks; ++c) {
           if (!mbar_wait(&tfull_bar[acc], acc_phase, 4)) { ok = false; break; }
           tcgen05_fence_after();
@@ -373,9 +389,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
           mbar_arrive(&tempty_bar[acc]);
           acc ^= 1u;
           if (acc == 0) acc_phase ^= 1u;
+          if (MODE == POD_OUT_HIDDEN && P.drop_thr != 0u && valid) dropout_bits_slice<NG>(P, n, pixel, col0, c, n_chunks, keep);
         }
         if (!ok || !valid) continue;
-        tile_epilogue<MODE, NG>(P, sum, n, pixel, col0);
+        tile_epilogue<MODE, NG>(P, sum, n, pixel, col0, keep);
       }
     }
   }
@@ -596,8 +613,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
       const bool valid = tile_ok && py < P.H && px < P.W;
       const int pixel = py * P.W + px;
       float sum[COLS];
+      uint32_t keep[(COLS + 31) / 32];
 #pragma unroll
       for (int i = 0; i < COLS; ++i) sum[i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < (COLS + 31) / 32; ++i) keep[i] = 0u;
       for (int c = 0; c < n_chunks; ++c) {
         if (!mbar_wait(&tfull_bar[acc], acc_phase, 14)) { ok = false; break; }
         tcgen05_fence_after();
@@ -618,9 +638,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
         mbar_arrive_cluster(acc ? te1 : te0);            // the leader's MMA thread tracks both CTAs
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
+        if (MODE == POD_OUT_HIDDEN && P.drop_thr != 0u && valid) dropout_bits_slice<NG>(P, n, pixel, col0, c, n_chunks, keep);
       }
       if (!ok || !valid) continue;
-      tile_epilogue<MODE, NG>(P, sum, n, pixel, col0);
+      tile_epilogue<MODE, NG>(P, sum, n, pixel, col0, keep);
     }
   }
 
