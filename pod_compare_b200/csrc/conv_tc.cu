@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cstring>
+#include <cstdlib>
 
 namespace tc {
 
@@ -26,7 +27,9 @@ constexpr int TILE_H = 8;
 constexpr int TILE_W = 16;
 constexpr int UMMA_K = 16;
 constexpr int ACC_COLS = 256;           // TMEM columns reserved per accumulator buffer
-constexpr int NUM_THREADS = 384;         // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
+constexpr int NUM_THREADS = 384;         // warpgroup 0: TMA producer (warp 0), MMA issuer + TMEM alloc (warp 1);
+                                         // warpgroups 1-2 (warps 4-11): epilogue.  setmaxnreg moves registers from
+                                         // warpgroup 0 to the epilogue warps so their 128 running sums stay in registers
 constexpr long long WAIT_LIMIT_CYCLES = 4000000000LL;   // ~2 s: bounded waits, never hang the box
 
 __device__ int g_status = 0;            // 0 ok; else code of the barrier wait that expired
@@ -37,6 +40,7 @@ struct Params {
   int tiles_x, tiles_y, num_tiles;
   int Cout, Cout_pad;
   int relu;
+  int dbg_skip_ld;      // debug: skip the TMEM drains (results invalid) to attribute chunk overhead
   int kb_per_chunk;     // K-blocks summed in the tensor core before an fp32 RN add in registers
   float acc_scale;      // 1 / (in_scale * w_scale)
   float out_scale;
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&tmem_base_s, 512);
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -288,6 +292,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
   const int tiles_per_map = P.tiles_x * P.tiles_y;
 
   if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0 && lane == 0) {
       // ================================ TMA producer ================================
       uint32_t stage = 0, phase = 0;
@@ -347,9 +352,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
     }
   } else {
     // ================================ epilogue ====================================
-    const int ew = warp - 4;
-    const int quad = ew & 3;                 // == warp % 4: the TMEM lane quadrant this warp may read
-    const int half = ew >> 2;                // column half (BN == 256 only)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int quad = warp & 3;               // the TMEM lane quadrant a warp may read is warp % 4
+    const int half = (warp - 4) >> 2;        // column half (BN == 256 only)
     if (half == 0 || BN == 256) {
       const int m = quad * 32 + lane;        // GEMM row == TMEM lane == pixel of the tile
       const int col0 = half * COLS;
@@ -372,6 +377,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
           const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_COLS + col0;
 #pragma unroll
           for (int g = 0; g < NG; g += 2) {
+            if (P.dbg_skip_ld) break;
             uint32_t r0[16], r1[16];
             __syncwarp();                          // tcgen05.ld is warp-collective (.sync.aligned)
             tmem_ld16(trow + g * 16, r0);
@@ -399,7 +405,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -521,7 +527,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc2(&tmem_base_s, 512);
+  if (warp == 1) tmem_alloc2(&tmem_base_s, 512);
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();                                   // peer barriers initialised, both TMEM halves allocated
@@ -536,6 +542,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
   const int num_pairs = (P.num_tiles + 1) >> 1;
   const int pair0 = (int)cluster_id_x(), pair_step = (int)nclusters_x();
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0 && lane == 0) {
     // ================================ TMA producer (both CTAs) ================================
     uint32_t stage = 0, phase = 0;
@@ -596,10 +604,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // ================================ epilogue (both CTAs) ====================================
-    const int ew = warp - 4;
-    const int quad = ew & 3, half = ew >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int quad = warp & 3, half = (warp - 4) >> 2;
     const int m = quad * 32 + lane;
     const int col0 = half * COLS;
     uint32_t acc = 0, acc_phase = 0;
@@ -624,6 +633,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
         const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_COLS + col0;
 #pragma unroll
         for (int g = 0; g < NG; g += 2) {
+          if (P.dbg_skip_ld) break;
           uint32_t r0[16], r1[16];
           __syncwarp();
           tmem_ld16(trow + g * 16, r0);
@@ -648,7 +658,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();                                   // nobody exits while the peer may still signal it
-  if (warp == 2) {
+  if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc2(tmem_base, 512);
   }
@@ -801,6 +811,7 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   P.Cout = a->Cout; P.Cout_pad = a->Cout_pad;
   P.relu = a->relu;
   P.kb_per_chunk = g_tc_taps * (a->Cin / BK);
+  P.dbg_skip_ld = getenv("POD_TC_DEBUG_SKIP_LD") ? 1 : 0;
   P.acc_scale = 1.0f / (a->in_scale * a->w_scale);
   P.out_scale = a->out_scale;
   P.bias = a->bias;
