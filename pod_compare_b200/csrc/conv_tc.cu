@@ -137,6 +137,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// one lane polls the mbarrier for the warp (256 spinning threads saturate the barrier unit)
+__device__ __forceinline__ bool warp_mbar_wait(uint64_t* bar, uint32_t parity, int code, int lane) {
+  int ok = 1;
+  if (lane == 0) ok = mbar_wait(bar, parity, code) ? 1 : 0;
+  return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): rows of ROW_BYTES
@@ -275,7 +291,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], EPI_THREADS);
+      mbar_init(&tempty_bar[i], EPI_THREADS / 32);        // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -372,27 +388,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
 #pragma unroll
         for (int i = 0; i < (COLS + 31) / 32; ++i) keep[i] = 0u;
         for (int c = 0; c < n_chunks; ++c) {
-          if (!mbar_wait(&tfull_bar[acc], acc_phase, 4)) { ok = false; break; }
+          if (!warp_mbar_wait(&tfull_bar[acc], acc_phase, 4, lane)) { ok = false; break; }
           tcgen05_fence_after();
           const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_COLS + col0;
+          if (!P.dbg_skip_ld) {
+            if (NG % 4 == 0) {
 #pragma unroll
-          for (int g = 0; g < NG; g += 2) {
-            if (P.dbg_skip_ld) break;
-            uint32_t r0[16], r1[16];
-            __syncwarp();                          // tcgen05.ld is warp-collective (.sync.aligned)
-            tmem_ld16(trow + g * 16, r0);
-            if (g + 1 < NG) tmem_ld16(trow + (g + 1) * 16, r1);
-            tmem_ld_wait();
+              for (int g = 0; g < NG; g += 4) {
+                uint32_t r0[32], r1[32];
+                tmem_ld32(trow + g * 16, r0);
+                tmem_ld32(trow + (g + 2) * 16, r1);
+                tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sum[g * 16 + i] = __fadd_rn(sum[g * 16 + i], __uint_as_float(r0[i]));
-            if (g + 1 < NG) {
+                for (int i = 0; i < 32; ++i) sum[g * 16 + i] = __fadd_rn(sum[g * 16 + i], __uint_as_float(r0[i]));
 #pragma unroll
-              for (int i = 0; i < 16; ++i) sum[(g + 1) * 16 + i] = __fadd_rn(sum[(g + 1) * 16 + i], __uint_as_float(r1[i]));
+                for (int i = 0; i < 32; ++i) sum[(g + 2) * 16 + i] = __fadd_rn(sum[(g + 2) * 16 + i], __uint_as_float(r1[i]));
+              }
+            } else {
+#pragma unroll
+              for (int g = 0; g < NG; ++g) {
+                uint32_t r0[16];
+                tmem_ld16(trow + g * 16, r0);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sum[g * 16 + i] = __fadd_rn(sum[g * 16 + i], __uint_as_float(r0[i]));
+              }
             }
           }
-          // all TMEM reads of this chunk are done: hand the accumulator back to the MMA warp
+          // all TMEM reads of this warp are done: one arrival per warp hands the accumulator back
           tcgen05_fence_before();
-          mbar_arrive(&tempty_bar[acc]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
           acc ^= 1u;
           if (acc == 0) acc_phase ^= 1u;
           if (MODE == POD_OUT_HIDDEN && P.drop_thr != 0u && valid) dropout_bits_slice<NG>(P, n, pixel, col0, c, n_chunks, keep);
@@ -523,7 +549,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 2 * EPI_THREADS);       // epilogue threads of BOTH CTAs
+      mbar_init(&tempty_bar[i], 2 * EPI_THREADS / 32);  // one arrival per epilogue warp of BOTH CTAs
     }
     fence_barrier_init();
   }
@@ -628,24 +654,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
 #pragma unroll
       for (int i = 0; i < (COLS + 31) / 32; ++i) keep[i] = 0u;
       for (int c = 0; c < n_chunks; ++c) {
-        if (!mbar_wait(&tfull_bar[acc], acc_phase, 14)) { ok = false; break; }
+        if (!warp_mbar_wait(&tfull_bar[acc], acc_phase, 14, lane)) { ok = false; break; }
         tcgen05_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_COLS + col0;
+        if (!P.dbg_skip_ld) {
 #pragma unroll
-        for (int g = 0; g < NG; g += 2) {
-          if (P.dbg_skip_ld) break;
-          uint32_t r0[16], r1[16];
-          __syncwarp();
-          tmem_ld16(trow + g * 16, r0);
-          tmem_ld16(trow + (g + 1) * 16, r1);
-          tmem_ld_wait();
+          for (int g = 0; g < NG; g += 4) {
+            uint32_t r0[32], r1[32];
+            tmem_ld32(trow + g * 16, r0);
+            tmem_ld32(trow + (g + 2) * 16, r1);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) sum[g * 16 + i] = __fadd_rn(sum[g * 16 + i], __uint_as_float(r0[i]));
+            for (int i = 0; i < 32; ++i) sum[g * 16 + i] = __fadd_rn(sum[g * 16 + i], __uint_as_float(r0[i]));
 #pragma unroll
-          for (int i = 0; i < 16; ++i) sum[(g + 1) * 16 + i] = __fadd_rn(sum[(g + 1) * 16 + i], __uint_as_float(r1[i]));
+            for (int i = 0; i < 32; ++i) sum[(g + 2) * 16 + i] = __fadd_rn(sum[(g + 2) * 16 + i], __uint_as_float(r1[i]));
+          }
         }
         tcgen05_fence_before();
-        mbar_arrive_cluster(acc ? te1 : te0);            // the leader's MMA thread tracks both CTAs
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc ? te1 : te0);   // the leader's MMA thread tracks both CTAs
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
         if (MODE == POD_OUT_HIDDEN && P.drop_thr != 0u && valid) dropout_bits_slice<NG>(P, n, pixel, col0, c, n_chunks, keep);
