@@ -117,8 +117,8 @@ typedef struct pod_conv_args {
   pod_dropout drop;
 } pod_conv_args;
 int pod_conv3x3_tc(const pod_conv_args* a, void* stream);
-/* Channels per pipeline stage of the tcgen05 kernel: 32 (SWIZZLE_64B operand tiles, deeper pipeline,
- * default) or 64 (SWIZZLE_128B).  Process-wide tuning knob; results are identical. */
+/* Channels per pipeline stage of the tcgen05 kernel: 64 (SWIZZLE_128B operand tiles, default) or
+ * 32 (SWIZZLE_64B, deeper pipeline).  Process-wide tuning knob; results are identical. */
 int pod_conv3x3_tc_set_kblock(int bk);
 /* 3x3 taps summed inside the tensor core before the partial sum is added in fp32 round-to-nearest by
  * the epilogue warps: 1 (default, most accurate), 3 or 9 (single chain; tcgen05 accumulates with

@@ -788,7 +788,7 @@ static int dispatch_bn(const Params& P, cudaStream_t st) {
 
 }  // namespace tc
 
-static int g_tc_bk = 32;      // K-block (channels per pipeline stage): 32 -> SWIZZLE_64B, 64 -> SWIZZLE_128B
+static int g_tc_bk = 64;      // K-block (channels per pipeline stage): 64 -> SWIZZLE_128B (default), 32 -> SWIZZLE_64B
 static int g_tc_taps = 1;     // taps per accumulation chunk (1, 3 or 9)
 
 extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_pair(int on) {

@@ -134,7 +134,7 @@ def test_tc_conv_raw_vs_fp64(shape, kblock, pair):
         assert not torch.isnan(got).any()
         assert err < 1e-5
     finally:
-        ops.set_conv_kblock(32)
+        ops.set_conv_kblock(64)
         ops.set_conv_pair(1)
 
 

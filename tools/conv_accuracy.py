@@ -35,4 +35,4 @@ for taps in (9, 3, 1):
         ops.set_conv_kblock(kb)
         print("tcgen05 fp16x3, chunk = %d tap(s), kblock %d:" % (taps, kb), stats(G.tc_conv_raw(x, w, b, False)))
 ops.set_conv_chunk_taps(1)
-ops.set_conv_kblock(32)
+ops.set_conv_kblock(64)
