@@ -284,8 +284,18 @@ def main():
                 n += 1
         if n:
             ach = tot_flop / (tot_ms / 1000.0) / 1e12
-            roof = {"bound": "tensor", "kernel": "k_conv3x3_tc<256,*,HIDDEN> (256->256 tower conv, fp16x3 split)",
-                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            traffic, traffic_note = None, None
+            try:
+                with open(os.path.join(ROOT, "profiles", "conv_traffic.json")) as f:
+                    tj = json.load(f)
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                traffic_note = ("dram read+write of ONE ncu-captured launch of this kernel (%d maps of %dx%dx256; algorithmic "
+                                "bytes of that launch: %.3e) -- %s" % (tj["maps"], tj["H"], tj["W"], tj["algorithmic_bytes"], tj["source"]))
+            except Exception:  # noqa: BLE001
+                pass
+            roof = {"bound": "tensor", "kernel": "tc::k_conv3x3_tc2<64,HIDDEN> (256->256 tower conv on CTA pairs, fp16x3 split)",
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                    "traffic_note": traffic_note,
                     "peak_source": peak_src, "launches": n, "avg_launch_ms": tot_ms / n,
                     "algorithmic_flop_per_launch": tot_flop / n,
                     "mma_tflops": 3.0 * ach, "mma_frac": 3.0 * ach / peak,
