@@ -193,7 +193,8 @@ int pod_decode_cov(const pod_decode_args* a, void* stream);
 
 /* ---- NMS / BayesOD fusion / rescale (inference_utils.py:12-54,292-334,374-425;
  *      probabilistic_inference.py:536-636; torchvision ops/boxes.py:51-120 + cpu/nms_kernel.cpp) ---
- * One CTA per image.  mode: 0 standard NMS, 1 BayesOD.  nms_variant: 0 per-class ("vanilla"),
+ * One CTA per image.  mode: 0 standard NMS, 1 BayesOD, 2 anchor statistics (inference_utils.py:57-162).
+ * nms_variant: 0 per-class ("vanilla"),
  * 1 coordinate-offset trick, 2 auto = torchvision's CPU rule (4*M > 4000 -> vanilla).
  * box_merge: 0 bayesian_inference, 1 covariance_intersection; cls_merge: 0 max_score,
  * 1 bayesian_inference (mean of member vectors).

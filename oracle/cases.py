@@ -41,6 +41,8 @@ CASES = {
                           "covariance_intersection"], "bayes_od", 1, [0], (96, 160), (96, 160), 17, 6),
     "ensembles_e3": (_VAR + _mode("ensembles") + ["PROBABILISTIC_INFERENCE.ENSEMBLES.RANDOM_SEED_NUMS", [0, 1000, 2000]],
                      "ensembles", 1, [0, 1000, 2000], (96, 160), (96, 160), 18, 7),
+    "anchorstats_var": (_VAR + _mode("anchor_statistics"), "anchor_statistics", 1, [0], (96, 160), (96, 160), 20, 9),
+    "anchorstats_base": ([] + _mode("anchor_statistics"), "anchor_statistics", 1, [1000], (96, 160), (96, 160), 21, 10),
     "fullcov_mc_n3": (_VAR + _FULL + _DROP + _mode("mc_dropout_ensembles") + _mc(3), "mc_dropout_ensembles", 3, [3000],
                       (96, 160), (96, 160), 19, 8),
 }

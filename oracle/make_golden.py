@@ -90,6 +90,11 @@ def planted_cases():
                 post = IU.probabilistic_detector_postprocess(out, 720, 1280)
                 key = "bod_%s_%s_" % ("ms" if cm == "max_score" else "avg", "bi" if bm == "bayesian_inference" else "ci")
                 d.update({key + k: v for k, v in R.instances_to_arrays(post).items()})
+        for use_cov, key in ((True, "ast_cov_"), (False, "ast_nocov_")):
+            t2 = (boxes, cov if use_cov else [], scores, classes, probs)
+            out = IU.general_anchor_statistics_postprocessing(input_im, t2, 0.5, 100, 0.9)
+            post = IU.probabilistic_detector_postprocess(out, 720, 1280)
+            d.update({key + k: v for k, v in R.instances_to_arrays(post).items()})
         np.savez_compressed(os.path.join(OUT, "planted_%s.npz" % tag), **d)
         print("planted %-6s M=%d std=%d" % (tag, boxes.shape[0], len(res)))
 

@@ -23,6 +23,7 @@ Reference lines followed (relative to /root/reference/src):
   aleatoric Monte-Carlo ... probabilistic_inference.py:344-385 ; inference_utils.py:510-547
   standard NMS ............ probabilistic_inference/inference_utils.py:12-54
   BayesOD ................. probabilistic_inference.py:536-636 ; inference_utils.py:292-334
+  anchor statistics ....... probabilistic_inference.py:409-428 ; inference_utils.py:57-162
   rescale / clip / cov .... inference_utils.py:374-425
   xyxy->xywh, JSON ........ inference_utils.py:428-502
 Third-party arithmetic restated from its published semantics (un-vendored, un-pinned
@@ -528,6 +529,36 @@ def bayes_od_post(c: Candidates, pp: PathParams, image_hw, nms_impl="torchvision
                       torch.empty(c.boxes.shape + (4,)), tuple(image_hw), keep)
 
 
+def anchor_statistics_post(c: Candidates, pp: PathParams, image_hw, nms_impl="torchvision"):
+    """inference_utils.py:57-162 (general_anchor_statistics_postprocessing)."""
+    iou = pairwise_iou(c.boxes, c.boxes)
+    keep = batched_nms(c.boxes, c.scores, c.classes, pp.nms_thresh, nms_impl)[: pp.max_dets]
+    member = iou[keep, :] > pp.affinity
+    has_cov = isinstance(c.cov, torch.Tensor) and len(c.cov) > 0
+    vec_list, box_list, cov_list = [], [], []
+    for row, center in zip(member, keep):
+        if row.sum(0) >= 2:
+            same = c.classes[row] == c.classes[center]
+            cluster = c.boxes[row, :][same, :]
+            mean = cluster.mean(0)
+            res = (cluster - mean).unsqueeze(2)
+            cov = torch.sum(torch.matmul(res, torch.transpose(res, 2, 1)), 0) / max((cluster.shape[0] - 1), 1.0)
+            if has_cov:
+                cov = cov + c.cov[row, :][same, :].mean(0)
+            vec = c.probs[row, :][same, :].mean(0)
+        else:
+            mean = c.boxes[center]
+            vec = c.probs[center]
+            cov = c.cov[center] if has_cov else 1e-4 * torch.eye(4, 4)
+        box_list.append(mean); cov_list.append(cov); vec_list.append(vec)
+    if len(box_list) > 0:
+        probs = torch.stack(vec_list, 0)
+        scores, classes = torch.max(probs, 1)
+        return Detections(torch.stack(box_list, 0), scores, classes, probs, torch.stack(cov_list, 0), tuple(image_hw), keep)
+    return Detections(c.boxes, torch.zeros(c.boxes.shape[0]), c.classes, c.probs, torch.empty(c.boxes.shape + (4,)),
+                      tuple(image_hw), keep)
+
+
 def detector_postprocess(d: Detections, out_h, out_w):
     """inference_utils.py:374-425 with detectron2 Boxes.scale/clip/nonempty."""
     sx, sy = out_w / d.image_size[1], out_h / d.image_size[0]
@@ -574,7 +605,8 @@ def detections_to_json(d: Detections, img_id, cat_mapping):
 # --------------------------------------------------------------------------------------
 def predict(feats, weight_sets, pp: PathParams, mode, image_hw, out_hw=None, n_mc=1, seed=0, image=0,
             dropout_mode="philox", nms_impl="torchvision", return_candidates=False, keep_diag=False):
-    """mode: 'standard_nms' | 'mc_dropout_ensembles' (pre_nms) | 'ensembles' (pre_nms) | 'bayes_od'.
+    """mode: 'standard_nms' | 'mc_dropout_ensembles' (pre_nms) | 'ensembles' (pre_nms) | 'bayes_od' |
+    'anchor_statistics'.
     weight_sets: list of unpacked heads (len E for 'ensembles', else 1). n_mc>1 enables MC-dropout
     (model.train(), probabilistic_inference.py:52-56)."""
     out_hw = out_hw or image_hw
@@ -594,6 +626,8 @@ def predict(feats, weight_sets, pp: PathParams, mode, image_hw, out_hw=None, n_m
     cand = anchorwise(outs, anchors, pp, seed, image, keep_diag=keep_diag)
     if mode == "bayes_od":
         det = bayes_od_post(cand, pp, image_hw, nms_impl)
+    elif mode == "anchor_statistics":
+        det = anchor_statistics_post(cand, pp, image_hw, nms_impl)
     else:
         det = standard_nms_post(cand, pp, image_hw, nms_impl)
     final = detector_postprocess(det, out_hw[0], out_hw[1])

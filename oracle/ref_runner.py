@@ -189,6 +189,9 @@ def run_reference(predictor, feats, image_hw, out_hw=None, seed=1, image_idx=0, 
         if stage == "final":
             out = predictor(input_im)
         elif stage == "anchorwise":
+            if predictor.inference_mode not in ("standard_nms", "mc_dropout_ensembles", "ensembles", "bayes_od",
+                                                "anchor_statistics"):
+                raise ValueError(predictor.inference_mode)
             if predictor.inference_mode == "ensembles":
                 outs = [m(input_im, return_anchorwise_output=True) for m in predictor.model_list]
                 out = predictor.retinanet_probabilistic_inference(

@@ -1,9 +1,11 @@
-// NMS, BayesOD clustering + Bayesian box fusion, and the final rescale/clip -- one CTA per image.
+// NMS, BayesOD clustering + Bayesian box fusion, anchor-statistics clustering, and the final
+// rescale/clip -- one CTA per image.
 //
 // Replaces, in /root/reference/src:
 //   probabilistic_inference/inference_utils.py:12-54      general_standard_nms_postprocessing
 //   probabilistic_inference/probabilistic_inference.py:536-636   post_processing_bayes_od
 //   probabilistic_inference/inference_utils.py:292-334    bounding_box_bayesian_inference
+//   probabilistic_inference/inference_utils.py:57-162     general_anchor_statistics_postprocessing
 //   probabilistic_inference/inference_utils.py:374-425    probabilistic_detector_postprocess
 // and the third-party ops they call: torchvision.ops.batched_nms (ops/boxes.py:51-120, both the
 // per-class and the coordinate-offset variants) over torchvision's CPU nms loop (strict '>',
@@ -336,6 +338,75 @@ __global__ void __launch_bounds__(NT) k_nms_fuse(pod_nms_args a, float sx, float
       } else {
         for (int k = lane; k < a.K; k += 32) det_probs[(int64_t)d * a.K + k] = probs[(int64_t)c * a.K + k];
       }
+    } else if (a.mode == 2) {
+      // anchor statistics (inference_utils.py:57-162): clusters with >= 2 IoU members take the mean box,
+      // sample covariance (+ mean member covariance) and mean probability vector of the SAME-CLASS members
+      const float area_c = box_area(cb.x, cb.y, cb.z, cb.w);
+      const int cls_c = classes[c];
+      const float aff = (float)a.affinity;
+      int n_all = 0, n_same = 0;
+      double sb[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int j = lane; j < M; j += 32) {
+        const float4 q = boxes[j];
+        if (!(d2_iou(cb, area_c, q, box_area(q.x, q.y, q.z, q.w)) > aff)) continue;
+        ++n_all;
+        if (classes[j] != cls_c) continue;
+        ++n_same;
+        sb[0] += q.x; sb[1] += q.y; sb[2] += q.z; sb[3] += q.w;
+      }
+      n_all = __reduce_add_sync(0xffffffffu, n_all);
+      n_same = __reduce_add_sync(0xffffffffu, n_same);
+      for (int e = 0; e < 4; ++e) sb[e] = warp_sum_d(sb[e]);
+      if (n_all >= 2 && n_same >= 1) {
+        float mean[4];
+        for (int e = 0; e < 4; ++e) mean[e] = (float)(sb[e] / (double)n_same);
+        double cc[16], mc[16];
+        for (int e = 0; e < 16; ++e) { cc[e] = 0.0; mc[e] = 0.0; }
+        for (int j = lane; j < M; j += 32) {
+          const float4 q = boxes[j];
+          if (!(d2_iou(cb, area_c, q, box_area(q.x, q.y, q.z, q.w)) > aff) || classes[j] != cls_c) continue;
+          const double r[4] = {(double)__fsub_rn(q.x, mean[0]), (double)__fsub_rn(q.y, mean[1]),
+                               (double)__fsub_rn(q.z, mean[2]), (double)__fsub_rn(q.w, mean[3])};
+          for (int x = 0; x < 4; ++x)
+            for (int y = 0; y < 4; ++y) cc[x * 4 + y] += r[x] * r[y];
+          if (a.has_cov)
+            for (int e = 0; e < 16; ++e) mc[e] += (double)covs[(int64_t)j * 16 + e];
+        }
+        const double den = n_same - 1 > 1 ? (double)(n_same - 1) : 1.0;
+        for (int e = 0; e < 16; ++e) {
+          cc[e] = warp_sum_d(cc[e]) / den;
+          mc[e] = warp_sum_d(mc[e]) / (double)n_same;
+          out_cov[e] = (double)((float)cc[e]) + (a.has_cov ? (double)((float)mc[e]) : 0.0);
+        }
+        for (int e = 0; e < 4; ++e) out_box[e] = mean[e];
+        float best = -1.f;
+        int bestk = 0;
+        for (int k = 0; k < a.K; ++k) {
+          float acc = 0.f;
+          for (int j = lane; j < M; j += 32) {
+            const float4 q = boxes[j];
+            if ((d2_iou(cb, area_c, q, box_area(q.x, q.y, q.z, q.w)) > aff) && classes[j] == cls_c)
+              acc += probs[(int64_t)j * a.K + k];
+          }
+          acc = warp_sum_f(acc) / (float)n_same;
+          if (lane == 0) det_probs[(int64_t)d * a.K + k] = acc;
+          if (acc > best) { best = acc; bestk = k; }
+        }
+        out_score = best;
+        out_cls = bestk;
+      } else {
+        if (!a.has_cov)
+          for (int e = 0; e < 16; ++e) out_cov[e] = (e % 5 == 0) ? (double)1e-4f : 0.0;
+        float best = -1.f;
+        int bestk = 0;
+        for (int k = 0; k < a.K; ++k) {
+          const float v = probs[(int64_t)c * a.K + k];
+          if (lane == 0) det_probs[(int64_t)d * a.K + k] = v;
+          if (v > best) { best = v; bestk = k; }
+        }
+        out_score = best;
+        out_cls = bestk;
+      }
     } else {
       for (int k = lane; k < a.K; k += 32) det_probs[(int64_t)d * a.K + k] = probs[(int64_t)c * a.K + k];
     }
@@ -412,7 +483,7 @@ extern "C" __attribute__((visibility("default"))) int pod_nms_fuse(const pod_nms
   POD_REQUIRE(a->B > 0 && a->cap > 0 && a->cap <= SORT_MAX, "pod_nms_fuse: cap must be in 1..%d", SORT_MAX);
   POD_REQUIRE(a->K > 0 && a->K <= MAX_K, "pod_nms_fuse: K must be in 1..%d", MAX_K);
   POD_REQUIRE(a->max_dets > 0 && a->max_dets <= MAX_DETS, "pod_nms_fuse: max_dets must be in 1..%d", MAX_DETS);
-  POD_REQUIRE(a->mode == 0 || (a->mode == 1 && a->has_cov), "pod_nms_fuse: BayesOD needs covariances");
+  POD_REQUIRE(a->mode == 0 || a->mode == 2 || (a->mode == 1 && a->has_cov), "pod_nms_fuse: mode must be 0, 1 (needs covariances) or 2");
   POD_REQUIRE(a->nms_variant >= 0 && a->nms_variant <= 2 && a->box_merge >= 0 && a->box_merge <= 1 && a->cls_merge >= 0 &&
                   a->cls_merge <= 1, "pod_nms_fuse: bad mode flags");
   POD_REQUIRE(a->in_h > 0 && a->in_w > 0 && a->out_h > 0 && a->out_w > 0, "pod_nms_fuse: bad image sizes");

@@ -248,9 +248,10 @@ class HeadEngine:
                               cand_idx, cand_cnt, seg, pc.box_num_samples, seed, image0, pc.reg_weights)
         return cand
 
-    def detections(self, cand, bayes_od, image_hw, out_hw, nms_variant=ops.NMS_AUTO):
+    def detections(self, cand, fuse_mode, image_hw, out_hw, nms_variant=ops.NMS_AUTO):
+        """fuse_mode: 0 standard NMS, 1 BayesOD, 2 anchor statistics."""
         pc = self.pc
-        return ops.nms_fuse(cand, 1 if bayes_od else 0, pc.nms_thresh, pc.affinity, pc.max_dets, image_hw, out_hw,
+        return ops.nms_fuse(cand, int(fuse_mode), pc.nms_thresh, pc.affinity, pc.max_dets, image_hw, out_hw,
                             nms_variant=nms_variant,
                             box_merge=0 if pc.box_merge == "bayesian_inference" else 1,
                             cls_merge=0 if pc.cls_merge == "max_score" else 1)

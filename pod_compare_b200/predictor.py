@@ -19,7 +19,7 @@ from . import _cabi, engine, ops
 from .engine import HeadEngine, HeadWeights, PathConfig
 from .structures import Boxes, Instances
 
-SUPPORTED_PRE_NMS_MODES = ("standard_nms", "mc_dropout_ensembles", "ensembles", "bayes_od")
+SUPPORTED_PRE_NMS_MODES = ("standard_nms", "mc_dropout_ensembles", "ensembles", "bayes_od", "anchor_statistics")
 
 
 def build_predictor(cfg):
@@ -167,8 +167,6 @@ class ProbabilisticPredictor:
             raise _cabi.PodError("no weights loaded: call load_weight_sets(state_dicts) first")
         mode = self.inference_mode
         pi = self.cfg.PROBABILISTIC_INFERENCE
-        if mode == 'anchor_statistics':
-            raise NotImplementedError("anchor_statistics post-processing is outside the rebuilt path (SURVEY 8f rank 1)")
         if mode == 'mc_dropout_ensembles' and pi.ENSEMBLES_DROPOUT.BOX_MERGE_MODE != 'pre_nms':
             raise NotImplementedError("post_nms MC-dropout merging is outside the rebuilt path (SURVEY 8f rank 1)")
         if mode == 'ensembles' and pi.ENSEMBLES.BOX_MERGE_MODE != 'pre_nms':
@@ -192,7 +190,7 @@ class ProbabilisticPredictor:
         else:
             raw, level_off = eng.head_eval(feats, members=[0])
         cand = eng.candidates(raw, level_off, anchors, seed, image0)
-        det = eng.detections(cand, mode == 'bayes_od', image_hw, out_hw)
+        det = eng.detections(cand, {'bayes_od': 1, 'anchor_statistics': 2}.get(mode, 0), image_hw, out_hw)
         res = self._to_instances(det, out_hw)
         if return_raw or return_candidates:
             return res, (raw if return_raw else None), cand, det
@@ -229,7 +227,7 @@ class RetinaNetProbabilisticPredictor(ProbabilisticPredictor):
         return self._single(input_im, 'bayes_od')
 
     def post_processing_anchor_statistics(self, input_im):
-        raise NotImplementedError("anchor_statistics post-processing is outside the rebuilt path (SURVEY 8f rank 1)")
+        return self._single(input_im, 'anchor_statistics')
 
     def _single(self, input_im, mode):
         saved = self.inference_mode

@@ -131,6 +131,18 @@ def test_nms_and_bayesod_on_planted_candidates(tag):
         r = O.standard_nms_post(sub, pp, (720, 1280), nms_impl="loop")
         n = int(det["keep_count"][0])
         assert np.array_equal(det["keep"][0, :n].cpu().numpy().astype(np.int64), r.keep.numpy())
+    # anchor statistics (mode 2), with and without candidate covariances
+    for use_cov, key in ((True, "ast_cov_"), (False, "ast_nocov_")):
+        cd2 = dict(cd)
+        cd2["has_cov"] = use_cov
+        det = ops.nms_fuse(cd2, 2, 0.5, 0.9, 100, (720, 1280), (720, 1280))
+        n = int(det["count"][0])
+        assert n == g[key + "boxes"].shape[0], key
+        assert np.array_equal(det["classes"][0, :n].cpu().numpy().astype(np.int64), g[key + "classes"]), key
+        assert np.allclose(det["scores"][0, :n].cpu().numpy(), g[key + "scores"], rtol=1e-5), key
+        assert np.allclose(det["probs"][0, :n].cpu().numpy(), g[key + "probs"], rtol=1e-5, atol=1e-8), key
+        assert np.allclose(det["boxes"][0, :n].cpu().numpy(), g[key + "boxes"], rtol=1e-6, atol=1e-3), key
+        assert _cov_close(det["cov"][0, :n].cpu().numpy(), g[key + "cov"], 1e-4), key
     # BayesOD, all merge-mode combinations
     for cm, ck in (("max_score", "ms"), ("bayesian_inference", "avg")):
         for bm, bk in (("bayesian_inference", "bi"), ("covariance_intersection", "ci")):
@@ -285,7 +297,7 @@ def test_end_to_end_matches_oracle(name):
     # the oracle here reproduces the committed reference fixture
     g = np.load(os.path.join(GOLDEN, "case_%s.npz" % name))
     assert np.allclose(ref_final.boxes.numpy(), g["final_boxes"], rtol=1e-4, atol=1e-3)
-    _compare_path(res[0], cand, det, ref_final, ref_cand, ref_det, pp, mode == "bayes_od")
+    _compare_path(res[0], cand, det, ref_final, ref_cand, ref_det, pp, mode in ("bayes_od", "anchor_statistics"))
 
 
 def test_batched_equals_single_image():
@@ -329,3 +341,47 @@ def test_reference_call_surface():
     pred.inference_mode = "nonsense"
     with pytest.raises(ValueError):
         pred(input_im)
+
+
+def test_full_size_path_properties_and_parity():
+    """BASELINE geometry (1280x720 -> 184 140 anchors), MC-dropout N=2 so the CPU oracle finishes in
+    seconds: parity of the whole path paired by anchor id, plus size-independent properties --
+    scores sorted, boxes inside the image, covariances symmetric positive definite, NMS idempotent
+    (re-running NMS on the survivors keeps all of them), results independent of batch position."""
+    import bench
+    H, W, N = 720, 1280, 2
+    cfg = bench.build_cfg(N)
+    pp = O.PathParams.from_cfg(cfg)
+    sd = S.make_head_state_dict(0, num_classes=7, use_dropout=True, cls_var=True, bbox_cov=True)
+    per_img = [S.make_features(0, i, H, W) for i in range(2)]
+    batch = [torch.cat([f[l] for f in per_img], 0) for l in range(5)]
+    pred = build_predictor(cfg)
+    pred.load_weight_sets(sd)
+    res, _, cand, det = pred.infer_from_features(batch, (H, W), (H, W), image0=0, seed=3, return_candidates=True)
+    assert int(cand["boxes"].shape[1]) == 4540 and int(cand["count"][0]) > 2000   # top-k binding on the big levels
+    for b in range(2):
+        r = res[b]
+        sc = r.scores.cpu().numpy()
+        assert len(r) == 100 and (np.diff(sc) <= 0).all()
+        bx = r.pred_boxes.tensor.cpu().numpy()
+        assert (bx[:, 0] >= 0).all() and (bx[:, 2] <= W).all() and (bx[:, 1] >= 0).all() and (bx[:, 3] <= H).all()
+        cv = r.pred_boxes_covariance.cpu().numpy().astype(np.float64)
+        assert np.allclose(cv, cv.transpose(0, 2, 1), rtol=1e-6, atol=1e-9)
+        assert (np.linalg.eigvalsh(cv) > 0).all()
+    # NMS idempotence on the survivors of image 0
+    n = len(res[0])
+    surv = {"boxes": det["boxes"][:1].contiguous(), "cov": det["cov"][:1].contiguous(), "scores": det["scores"][:1].contiguous(),
+            "classes": det["classes"][:1].contiguous(), "probs": det["probs"][:1].contiguous(),
+            "count": det["count"][:1].contiguous(), "has_cov": True}
+    again = ops.nms_fuse(surv, 0, 0.5, 0.9, 100, (H, W), (H, W))
+    assert int(again["keep_count"][0]) == n and again["keep"][0, :n].cpu().tolist() == list(range(n))
+    # batch position independence
+    r1 = pred.infer_from_features(per_img[1], (H, W), (H, W), image0=1, seed=3)[0]
+    assert torch.equal(r1.pred_boxes.tensor, res[1].pred_boxes.tensor) and torch.equal(r1.scores, res[1].scores)
+    # parity with the oracle for image 0
+    torch.set_num_threads(os.cpu_count())
+    ref_final, ref_cand, ref_det = O.predict(per_img[0], [O.unpack_head(sd, pp)], pp, "mc_dropout_ensembles", (H, W), n_mc=N,
+                                             seed=3, image=0, return_candidates=True, keep_diag=True)
+    one = {k: (v[:1] if isinstance(v, torch.Tensor) else v) for k, v in cand.items()}
+    one_det = {k: (v[:1] if isinstance(v, torch.Tensor) else v) for k, v in det.items()}
+    _compare_path(res[0], one, one_det, ref_final, ref_cand, ref_det, pp, False)

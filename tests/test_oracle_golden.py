@@ -70,6 +70,15 @@ def test_planted_postprocessing_matches_reference_fixture(tag, golden_dir):
         assert np.array_equal(d.scores.numpy(), g["std_scores"])
         assert np.array_equal(d.classes.numpy(), g["std_classes"])
         assert np.array_equal(d.cov.numpy(), g["std_cov"])
+    for use_cov, key in ((True, "ast_cov_"), (False, "ast_nocov_")):
+        c2 = O.Candidates(cand.boxes, cand.cov if use_cov else None, cand.scores, cand.classes, cand.probs,
+                          cand.anchor_ids, cand.level_counts)
+        d = O.detector_postprocess(O.anchor_statistics_post(c2, pp, (720, 1280)), 720, 1280)
+        assert np.array_equal(d.boxes.numpy(), g[key + "boxes"]), key
+        assert np.array_equal(d.scores.numpy(), g[key + "scores"]), key
+        assert np.array_equal(d.classes.numpy(), g[key + "classes"]), key
+        assert np.array_equal(d.probs.numpy(), g[key + "probs"]), key
+        assert np.array_equal(d.cov.numpy(), g[key + "cov"]), key
     for cm, ck in (("max_score", "ms"), ("bayesian_inference", "avg")):
         for bm, bk in (("bayesian_inference", "bi"), ("covariance_intersection", "ci")):
             pp.cls_merge, pp.box_merge = cm, bm
