@@ -147,8 +147,11 @@ int pod_sample_mean_q1(const float* x, int B, int S, int64_t n, float* out, void
  *   without     : sigmoid(mu)
  * then max/argmax over K.  probs (B,R,K), score (B,R), cls (B,R) int32. */
 int pod_scores(const float* logits, const float* logvar /*nullable*/, int B, int R, int K, int n_levels,
-               const int* level_off /*host, n_levels+1*/, int draws, uint64_t seed, int image0,
+               const int* level_off /*host, n_levels+1*/, int draws, uint64_t seed, int image0, int runs,
                float* probs, float* score, int* cls, void* stream);
+/* `runs` (>= 1): row b of the batch is run (b % runs) of image image0 + b / runs -- the post-NMS merge modes
+ * evaluate every MC sample / ensemble member as its own inference with its own noise draws
+ * (probabilistic_inference.py:444-461,506-511); the run index enters the Philox counter. */
 /* Per (image, level): the min(topk, n_l) highest scores, descending, ties -> lower anchor index,
  * then those > thresh.  cand_idx (B, cap) holds GLOBAL anchor ids, level l's segment starts at
  * seg_off[l] (host array, n_levels+1, seg_off[l+1]-seg_off[l] = min(topk, n_l)); cand_cnt (B, n_levels). */
@@ -180,6 +183,7 @@ typedef struct pod_decode_args {
   int box_draws;
   uint64_t seed;
   int image0;
+  int runs;   /* see pod_scores */
   float wx, wy, ww, wh;
   float* out_boxes;
   float* out_cov;
@@ -225,8 +229,33 @@ typedef struct pod_nms_args {
   int* keep;
   int* keep_count;
   int* det_src;  /* (B,max_dets): candidate index each FINAL detection row came from */
+  int skip_post; /* 1: stop after NMS/fusion (no rescale, clip, nonempty filter, covariance conditioning) */
 } pod_nms_args;
 int pod_nms_fuse(const pod_nms_args* a, void* stream);
+
+/* ---- post-NMS merging of per-run detections (inference_utils.py:165-289,
+ *      general_black_box_ensembles_post_processing; reached from probabilistic_inference.py:444-481,506-534) ----
+ * in : per-run detections from pod_nms_fuse(skip_post=1), rows b*runs + r: det_* (B*runs, max_dets, ...), det_count.
+ * The runs of an image are concatenated run-major; boxes are clustered sequentially (seed i unless already a
+ * member of an earlier cluster; members = IoU >= affinity and same class); every cluster yields the mean box,
+ * sample covariance (+ mean member covariance), mean probability vector and its max/argmax.
+ * out: cluster_* (B, runs*max_dets, ...) + cluster_count (B): a candidate set for pod_nms_fuse (final NMS + rescale). */
+typedef struct pod_merge_args {
+  const float* det_boxes;
+  const float* det_cov;
+  const float* det_probs;
+  const int* det_classes;
+  const int* det_count;
+  int B, runs, max_dets, K;
+  double affinity;
+  float* out_boxes;
+  float* out_cov;
+  float* out_scores;
+  int* out_classes;
+  float* out_probs;
+  int* out_count;
+} pod_merge_args;
+int pod_cluster_merge(const pod_merge_args* a, void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,12 @@ CASES = {
                      "ensembles", 1, [0, 1000, 2000], (96, 160), (96, 160), 18, 7),
     "anchorstats_var": (_VAR + _mode("anchor_statistics"), "anchor_statistics", 1, [0], (96, 160), (96, 160), 20, 9),
     "anchorstats_base": ([] + _mode("anchor_statistics"), "anchor_statistics", 1, [1000], (96, 160), (96, 160), 21, 10),
+    "mcdrop_post_n3": (_VAR + _DROP + _mode("mc_dropout_ensembles") + _mc(3) +
+                       ["PROBABILISTIC_INFERENCE.ENSEMBLES_DROPOUT.BOX_MERGE_MODE", "post_nms"], "mc_dropout_ensembles", 3, [0],
+                       (96, 160), (96, 160), 22, 11),
+    "ensembles_post_e3": (_VAR + _mode("ensembles") + ["PROBABILISTIC_INFERENCE.ENSEMBLES.RANDOM_SEED_NUMS", [0, 1000, 2000],
+                          "PROBABILISTIC_INFERENCE.ENSEMBLES.BOX_MERGE_MODE", "post_nms"], "ensembles", 1, [0, 1000, 2000],
+                          (96, 160), (96, 160), 23, 12),
     "fullcov_mc_n3": (_VAR + _FULL + _DROP + _mode("mc_dropout_ensembles") + _mc(3), "mc_dropout_ensembles", 3, [3000],
                       (96, 160), (96, 160), 19, 8),
 }
@@ -56,3 +62,8 @@ def build_cfg(name):
     cfg.MODEL.DEVICE = "cpu"
     cfg.freeze()
     return cfg
+
+
+def is_post_nms(name):
+    opts = CASES[name][0]
+    return any(isinstance(o, str) and o == "post_nms" for o in opts)

@@ -47,6 +47,12 @@ def model_case(name):
     pred = R.build_reference_predictor(cfg, sds if len(sds) > 1 else sds[0])
     feats = S.make_features(0, img, hw[0], hw[1])
     final, _ = R.run_reference(pred, feats, hw, out_hw=out_hw, seed=seed, image_idx=img, stage="final")
+    if C.is_post_nms(name):
+        d = {"final_" + k: v for k, v in R.instances_to_arrays(final).items()}
+        d["feats_checksum"] = feats_checksum(feats)
+        np.savez_compressed(os.path.join(OUT, "case_%s.npz" % name), **d)
+        print("case %-20s detections=%3d (post-NMS merge)" % (name, len(final)))
+        return
     aw, rng = R.run_reference(pred, feats, hw, out_hw=out_hw, seed=seed, image_idx=img, stage="anchorwise")
     boxes, cov, prob, cls, vec = aw
     d = {"final_" + k: v for k, v in R.instances_to_arrays(final).items()}

@@ -13,10 +13,12 @@ that contract; only tests/, bench.py's cpu_baseline leg and smoke() import it.
 Stream layout (key = (seed_lo, seed_hi ^ STREAM), counter = (c0, c1, c2, c3)):
   STREAM_DROPOUT : c0 = (pixel*C + channel)//4, c1 = level | layer<<8 | tower<<16 | pass<<24,
                    c2 = sample, c3 = image; word i -> channel 4*c0%C + i; keep iff word >= floor(p*2^32)
-  STREAM_LOGIT   : c0 = (anchor*K + k)//4 (row-major over (HWA, K) of one level), c1 = level,
+  STREAM_LOGIT   : c0 = (anchor*K + k)//4 (row-major over (HWA, K) of one level), c1 = level | run<<8,
                    c2 = draw j, c3 = image; 4 words -> 4 normals (two Box-Muller pairs)
-  STREAM_BOX     : c0 = global anchor id (level offset + index in level), c1 = 0,
+  STREAM_BOX     : c0 = global anchor id (level offset + index in level), c1 = run,
                    c2 = draw j, c3 = image; 4 words -> eps[j, m, 0..3]
+`run` is 0 except in the post-NMS merge modes, where every MC sample / ensemble member is its own
+inference with its own draws (probabilistic_inference.py:444-461,506-511).
 Uniforms use the top 23 bits, u = ((w >> 9) + 0.5) * 2^-23, which is exact in fp32.
 Normals: r = sqrt(-2 ln u_a), n_a = r cos(2 pi u_b), n_b = r sin(2 pi u_b); the CPU
 side evaluates this in float64 and rounds once to fp32 (the GPU evaluates in fp32,
@@ -85,26 +87,26 @@ def dropout_keep_mask(seed, image, sample, pass_, tower, layer, level, H, W, C, 
     return words >= np.uint32(dropout_threshold(p))
 
 
-def logit_normals(seed, image, level, draws, n_anchor, K):
+def logit_normals(seed, image, level, draws, n_anchor, K, run=0):
     """fp32 array (draws, n_anchor, K) -- the eps of Normal.rsample((draws,))."""
     k0, k1 = _key(seed, STREAM_LOGIT)
     n = n_anchor * K
     nq = (n + 3) // 4
     q = np.arange(nq, dtype=np.uint64)[None, :]
     j = np.arange(draws, dtype=np.uint64)[:, None]
-    w0, w1, w2, w3 = philox4x32(q, level, j, image, k0, k1)
+    w0, w1, w2, w3 = philox4x32(q, (level & 0xFF) | ((run & 0xFFFFFF) << 8), j, image, k0, k1)
     n0, n1 = box_muller(w0, w1)
     n2, n3 = box_muller(w2, w3)
     out = np.stack([n0, n1, n2, n3], axis=2).reshape(draws, nq * 4)[:, :n]
     return np.ascontiguousarray(out.reshape(draws, n_anchor, K))
 
 
-def box_normals(seed, image, anchor_ids, draws):
+def box_normals(seed, image, anchor_ids, draws, run=0):
     """fp32 array (draws, M, 4) -- the eps of MultivariateNormal.rsample((draws,))."""
     k0, k1 = _key(seed, STREAM_BOX)
     a = np.asarray(anchor_ids, dtype=np.uint64)[None, :]
     j = np.arange(draws, dtype=np.uint64)[:, None]
-    w0, w1, w2, w3 = philox4x32(a, 0, j, image, k0, k1)
+    w0, w1, w2, w3 = philox4x32(a, run, j, image, k0, k1)
     n0, n1 = box_muller(w0, w1)
     n2, n3 = box_muller(w2, w3)
     return np.ascontiguousarray(np.stack([n0, n1, n2, n3], axis=2))

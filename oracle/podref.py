@@ -22,6 +22,7 @@ Reference lines followed (relative to /root/reference/src):
   epistemic covariance .... probabilistic_inference.py:322-331 ; inference_utils.py:337-371
   aleatoric Monte-Carlo ... probabilistic_inference.py:344-385 ; inference_utils.py:510-547
   standard NMS ............ probabilistic_inference/inference_utils.py:12-54
+  post-NMS merging ........ probabilistic_inference.py:444-481,506-534 ; inference_utils.py:165-289
   BayesOD ................. probabilistic_inference.py:536-636 ; inference_utils.py:292-334
   anchor statistics ....... probabilistic_inference.py:409-428 ; inference_utils.py:57-162
   rescale / clip / cov .... inference_utils.py:374-425
@@ -306,7 +307,7 @@ class Candidates:
 
 
 def anchorwise(outputs_list, anchors, pp: PathParams, seed=0, image=0, keep_diag=False, stable_topk=True,
-               normal_mode="philox"):
+               normal_mode="philox", run=0):
     """outputs_list: list over samples/members of raw-output dicts (len 1 => no epistemic part).
     normal_mode 'torch' draws the logit / box noise from torch's own generator, as the reference does
     (CPU-baseline timing only; parity runs use the Philox streams)."""
@@ -333,7 +334,7 @@ def anchorwise(outputs_list, anchors, pp: PathParams, seed=0, image=0, keep_diag
                 eps = torch.randn((pp.cls_var_num_samples,) + tuple(box_cls.shape))
             else:
                 eps = torch.from_numpy(philox.logit_normals(seed, image, i, pp.cls_var_num_samples,
-                                                            box_cls.shape[0], box_cls.shape[1]))
+                                                            box_cls.shape[0], box_cls.shape[1], run=run))
             draws = box_cls + eps * torch.sqrt(torch.exp(logvar))       # Normal.rsample: loc + eps*scale
             box_cls = torch.mean(draws.sigmoid_(), 0)
         else:
@@ -373,7 +374,7 @@ def anchorwise(outputs_list, anchors, pp: PathParams, seed=0, image=0, keep_diag
         if normal_mode == "torch":
             eps = torch.randn((S, delta.shape[0], 4))
         else:
-            eps = torch.from_numpy(philox.box_normals(seed, image, ids, S))           # (S,M,4)
+            eps = torch.from_numpy(philox.box_normals(seed, image, ids, S, run=run))  # (S,M,4)
         draws = delta + torch.matmul(L, eps.unsqueeze(-1)).squeeze(-1)                  # loc + L eps
         draws = torch.transpose(torch.transpose(draws, 0, 1), 1, 2)                     # (M,4,S)
         anc_s = torch.repeat_interleave(anc.unsqueeze(2), S, dim=2)
@@ -559,6 +560,41 @@ def anchor_statistics_post(c: Candidates, pp: PathParams, image_hw, nms_impl="to
                       tuple(image_hw), keep)
 
 
+def black_box_post(dets: List[Detections], pp: PathParams, image_hw, nms_impl="torchvision"):
+    """inference_utils.py:165-289 (general_black_box_ensembles_post_processing): merge of per-run,
+    post-NMS detections by sequential IoU clustering, then one more NMS."""
+    boxes = torch.cat([d.boxes for d in dets], 0)
+    covs = torch.cat([d.cov for d in dets], 0)
+    probs = torch.cat([d.probs for d in dets], 0)
+    cls = torch.cat([d.classes for d in dets], 0)
+    iou = pairwise_iou(boxes, boxes)
+    clusters = []
+    for i in range(iou.shape[0]):
+        if i != 0:
+            allc = torch.cat(clusters, 0)
+            if (allc == i).any():
+                continue
+        clusters.extend(torch.where((iou[i, :] >= pp.affinity) & (cls == cls[i])))
+    box_list, cov_list, vec_list = [], [], []
+    for cl in clusters:
+        bc, cc = boxes[cl], covs[cl]
+        if bc.shape[0] >= 2:
+            mean = bc.mean(0)
+            res = (bc - mean).unsqueeze(2)
+            cov = torch.sum(torch.matmul(res, torch.transpose(res, 2, 1)), 0) / (bc.shape[0] - 1)
+            cov = cov + cc.mean(0)
+            box_list.append(mean); cov_list.append(cov); vec_list.append(probs[cl].mean(0))
+        else:
+            box_list.append(boxes[cl].mean(0)); cov_list.append(covs[cl].mean(0)); vec_list.append(probs[cl].mean(0))
+    if len(box_list) > 0:
+        pv = torch.stack(vec_list, 0)
+        score, classes = torch.max(pv, 1)
+        mb = torch.stack(box_list, 0)
+        keep = batched_nms(mb, score, classes, pp.nms_thresh, nms_impl)[: pp.max_dets]
+        return Detections(mb[keep], score[keep], classes[keep], pv[keep], torch.stack(cov_list, 0)[keep], tuple(image_hw), keep)
+    return Detections(boxes, torch.zeros(boxes.shape[0]), cls, probs, torch.empty(boxes.shape + (4,)), tuple(image_hw), None)
+
+
 def detector_postprocess(d: Detections, out_h, out_w):
     """inference_utils.py:374-425 with detectron2 Boxes.scale/clip/nonempty."""
     sx, sy = out_w / d.image_size[1], out_h / d.image_size[0]
@@ -604,7 +640,7 @@ def detections_to_json(d: Detections, img_id, cat_mapping):
 # whole path, one image:  features -> detections   (predictor.__call__, :86-111)
 # --------------------------------------------------------------------------------------
 def predict(feats, weight_sets, pp: PathParams, mode, image_hw, out_hw=None, n_mc=1, seed=0, image=0,
-            dropout_mode="philox", nms_impl="torchvision", return_candidates=False, keep_diag=False):
+            dropout_mode="philox", nms_impl="torchvision", return_candidates=False, keep_diag=False, post_nms=False):
     """mode: 'standard_nms' | 'mc_dropout_ensembles' (pre_nms) | 'ensembles' (pre_nms) | 'bayes_od' |
     'anchor_statistics'.
     weight_sets: list of unpacked heads (len E for 'ensembles', else 1). n_mc>1 enables MC-dropout
@@ -623,6 +659,18 @@ def predict(feats, weight_sets, pp: PathParams, mode, image_hw, out_hw=None, n_m
         # (MC_DROPOUT.ENABLE with NUM_RUNS == 1), which the shipped configs never do.
         drop = DropoutSource("off", 0.0)
         outs = [head_outputs(feats, weight_sets[0], pp, drop)]
+    if post_nms:
+        # probabilistic_inference.py:444-481 / 506-534: every run is a complete single-sample inference
+        # (own noise draws, no epistemic term) followed by standard NMS; the runs are merged afterwards
+        runs = []
+        for r, o in enumerate(outs):
+            c = anchorwise([o], anchors, pp, seed, image, run=r)
+            runs.append(standard_nms_post(c, pp, image_hw, nms_impl))
+        det = black_box_post(runs, pp, image_hw, nms_impl)
+        final = detector_postprocess(det, out_hw[0], out_hw[1])
+        if return_candidates:
+            return final, runs, det
+        return final
     cand = anchorwise(outs, anchors, pp, seed, image, keep_diag=keep_diag)
     if mode == "bayes_od":
         det = bayes_od_post(cand, pp, image_hw, nms_impl)

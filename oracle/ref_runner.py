@@ -70,6 +70,7 @@ class RngInjector:
         self.n_dropout = 0
         self.n_normal = 0
         self.cand_ids = []                            # global anchor ids in concatenation order
+        self._ids_start = 0
         self.level_sizes = None                       # anchors per level (set by the runner)
         self.log = {"dropout_calls": 0, "normal_calls": 0, "mvn_calls": 0}
 
@@ -95,17 +96,20 @@ class RngInjector:
     # --- Normal.rsample((S,)) -> _standard_normal((S, HWA, K)) ----------------------------
     def normal_eps(self, shape, dtype, device):
         S, n_anchor, K = shape
-        level = self.n_normal % self.n_levels
+        run, level = divmod(self.n_normal, self.n_levels)      # one call per level per inference run
         self.n_normal += 1
         self.log["normal_calls"] += 1
-        return torch.from_numpy(philox.logit_normals(self.seed, self.image, level, S, n_anchor, K)).to(dtype)
+        return torch.from_numpy(philox.logit_normals(self.seed, self.image, level, S, n_anchor, K, run=run)).to(dtype)
 
     # --- MultivariateNormal.rsample((1000,)) -> _standard_normal((1000, M, 4)) ------------
     def mvn_eps(self, shape, dtype, device):
         S, M, D = shape
-        assert D == 4 and M == len(self.cand_ids), (shape, len(self.cand_ids))
+        ids = self.cand_ids[self._ids_start:]                  # candidates gathered since the previous run
+        assert D == 4 and M == len(ids), (shape, len(ids))
+        self._ids_start = len(self.cand_ids)
+        run = self.log["mvn_calls"]
         self.log["mvn_calls"] += 1
-        return torch.from_numpy(philox.box_normals(self.seed, self.image, self.cand_ids, S)).to(dtype)
+        return torch.from_numpy(philox.box_normals(self.seed, self.image, ids, S, run=run)).to(dtype)
 
 
 @contextlib.contextmanager

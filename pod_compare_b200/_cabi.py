@@ -15,6 +15,7 @@ EXPORTS = [
     "pod_nchw_to_nhwc_split", "pod_nchw_to_nhwc_f32", "pod_pack_conv_weight", "pod_pack_conv_weight_f32",
     "pod_mask_expand_split", "pod_conv3x3_tc", "pod_conv3x3_tc_set_kblock", "pod_conv3x3_tc_set_chunk_taps", "pod_conv3x3_tc_set_pair", "pod_conv3x3_tc_status",
     "pod_conv3x3_simt", "pod_sample_mean_q1", "pod_scores", "pod_topk_levels", "pod_decode_cov", "pod_nms_fuse",
+    "pod_cluster_merge",
 ]
 
 POD_OUT_HIDDEN, POD_OUT_RAW = 0, 1
@@ -44,7 +45,7 @@ class DecodeArgs(C.Structure):
                 ("score", C.c_void_p), ("cls", C.c_void_p), ("cand_idx", C.c_void_p), ("cand_cnt", C.c_void_p),
                 ("B", C.c_int), ("R", C.c_int), ("K", C.c_int), ("n_levels", C.c_int), ("cap", C.c_int),
                 ("seg_off_host", C.POINTER(C.c_int)), ("box_draws", C.c_int), ("seed", C.c_uint64),
-                ("image0", C.c_int), ("wx", C.c_float), ("wy", C.c_float), ("ww", C.c_float), ("wh", C.c_float),
+                ("image0", C.c_int), ("runs", C.c_int), ("wx", C.c_float), ("wy", C.c_float), ("ww", C.c_float), ("wh", C.c_float),
                 ("out_boxes", C.c_void_p), ("out_cov", C.c_void_p), ("out_scores", C.c_void_p),
                 ("out_classes", C.c_void_p), ("out_probs", C.c_void_p), ("out_count", C.c_void_p),
                 ("out_anchor", C.c_void_p)]
@@ -58,7 +59,14 @@ class NmsArgs(C.Structure):
                 ("in_h", C.c_int), ("in_w", C.c_int), ("out_h", C.c_int), ("out_w", C.c_int),
                 ("det_boxes", C.c_void_p), ("det_cov", C.c_void_p), ("det_scores", C.c_void_p),
                 ("det_classes", C.c_void_p), ("det_probs", C.c_void_p), ("det_count", C.c_void_p),
-                ("keep", C.c_void_p), ("keep_count", C.c_void_p), ("det_src", C.c_void_p)]
+                ("keep", C.c_void_p), ("keep_count", C.c_void_p), ("det_src", C.c_void_p), ("skip_post", C.c_int)]
+
+
+class MergeArgs(C.Structure):
+    _fields_ = [("det_boxes", C.c_void_p), ("det_cov", C.c_void_p), ("det_probs", C.c_void_p), ("det_classes", C.c_void_p),
+                ("det_count", C.c_void_p), ("B", C.c_int), ("runs", C.c_int), ("max_dets", C.c_int), ("K", C.c_int),
+                ("affinity", C.c_double), ("out_boxes", C.c_void_p), ("out_cov", C.c_void_p), ("out_scores", C.c_void_p),
+                ("out_classes", C.c_void_p), ("out_probs", C.c_void_p), ("out_count", C.c_void_p)]
 
 
 _lib = None
@@ -95,11 +103,12 @@ def load_library():
                                      C.c_int, C.POINTER(Dropout), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     lib.pod_sample_mean_q1.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
     lib.pod_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int,
-                               C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                               C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pod_topk_levels.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pod_decode_cov.argtypes = [C.POINTER(DecodeArgs), C.c_void_p]
     lib.pod_nms_fuse.argtypes = [C.POINTER(NmsArgs), C.c_void_p]
+    lib.pod_cluster_merge.argtypes = [C.POINTER(MergeArgs), C.c_void_p]
     _lib = lib
     return lib
 

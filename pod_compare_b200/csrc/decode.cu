@@ -117,9 +117,10 @@ __global__ void __launch_bounds__(256) k_decode(pod_decode_args a, SegTable st, 
       L[1][0] = rv[4]; L[2][0] = rv[5]; L[2][1] = rv[6]; L[3][0] = rv[7]; L[3][1] = rv[8]; L[3][2] = rv[9];
     }
     const bool diag = a.cov_dims <= 4;
-    const uint32_t image = (uint32_t)(a.image0 + b);
+    const uint32_t image = (uint32_t)(a.image0 + b / a.runs);
+    const uint32_t run = (uint32_t)(b % a.runs);
     auto gen = [&](int j, float x[4]) {
-      const uint4 w = philox4x32_10((uint32_t)gid, 0u, (uint32_t)j, image, key);
+      const uint4 w = philox4x32_10((uint32_t)gid, run, (uint32_t)j, image, key);
       float z[4], d[4];
       pod_box_muller(w.x, w.y, z[0], z[1]);
       pod_box_muller(w.z, w.w, z[2], z[3]);
@@ -181,6 +182,7 @@ extern "C" __attribute__((visibility("default"))) int pod_decode_cov(const pod_d
   POD_REQUIRE(a->B > 0 && a->R > 0 && a->K > 0 && a->n_levels > 0 && a->n_levels <= MAX_LEVELS, "pod_decode_cov: bad shape");
   POD_REQUIRE(!a->mean_regvar || a->cov_dims == 4 || a->cov_dims == 10, "pod_decode_cov: cov_dims must be 4 or 10");
   POD_REQUIRE(!a->mean_regvar || a->box_draws > 1, "pod_decode_cov: box_draws must be > 1");
+  POD_REQUIRE(a->runs >= 1, "pod_decode_cov: runs must be >= 1");
   POD_REQUIRE(a->wx > 0 && a->wy > 0 && a->ww > 0 && a->wh > 0, "pod_decode_cov: regression weights must be positive");
   SegTable st;
   st.n_levels = a->n_levels;

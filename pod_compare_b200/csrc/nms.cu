@@ -424,7 +424,13 @@ __global__ void __launch_bounds__(NT) k_nms_fuse(pod_nms_args a, float sx, float
   //  thread reads its own record before any thread writes -- two phases separated by a barrier)
   float bx[4] = {0.f, 0.f, 0.f, 0.f}, cv[16], pr_score = 0.f;
   int pr_cls = 0, flag = 0;
-  if (tid < nk) {
+  if (tid < nk && a.skip_post) {
+    for (int e = 0; e < 4; ++e) bx[e] = s_out_box[tid][e];
+    for (int e = 0; e < 16; ++e) cv[e] = det_cov[(int64_t)tid * 16 + e];
+    flag = 1;
+    pr_score = s_out_score[tid];
+    pr_cls = s_out_cls[tid];
+  } else if (tid < nk) {
     bx[0] = __fmul_rn(s_out_box[tid][0], sx);
     bx[1] = __fmul_rn(s_out_box[tid][1], sy);
     bx[2] = __fmul_rn(s_out_box[tid][2], sx);

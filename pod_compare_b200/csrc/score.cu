@@ -16,7 +16,7 @@ __device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.0f, 
 
 // one thread = 4 consecutive anchors of one level = K Philox quads per draw
 __global__ void k_scores(const float* __restrict__ logits, const float* __restrict__ logvar, int B, int R, int K,
-                         LevelTable lt, int draws, PhiloxKey key, int image0, float* __restrict__ probs,
+                         LevelTable lt, int draws, PhiloxKey key, int image0, int runs, float* __restrict__ probs,
                          float* __restrict__ score, int* __restrict__ cls) {
   const int groups = lt.grp_off[lt.n_levels];
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)B * groups;
@@ -45,7 +45,8 @@ __global__ void k_scores(const float* __restrict__ logits, const float* __restri
       }
       if (logvar) {
         for (int j = 0; j < draws; ++j) {
-          const uint4 w = philox4x32_10((uint32_t)(e >> 2), (uint32_t)level, (uint32_t)j, (uint32_t)(image0 + b), key);
+          const uint4 w = philox4x32_10((uint32_t)(e >> 2), (uint32_t)level | ((uint32_t)(b % runs) << 8), (uint32_t)j,
+                                        (uint32_t)(image0 + b / runs), key);
           float z[4];
           pod_box_muller(w.x, w.y, z[0], z[1]);
           pod_box_muller(w.z, w.w, z[2], z[3]);
@@ -208,8 +209,9 @@ int fill_table(LevelTable& lt, int n_levels, const int* level_off, const int* se
 }  // namespace
 
 extern "C" __attribute__((visibility("default"))) int pod_scores(const float* logits, const float* logvar, int B, int R, int K, int n_levels,
-                          const int* level_off, int draws, uint64_t seed, int image0, float* probs, float* score, int* cls,
+                          const int* level_off, int draws, uint64_t seed, int image0, int runs, float* probs, float* score, int* cls,
                           void* stream) {
+  POD_REQUIRE(runs >= 1, "pod_scores: runs must be >= 1");
   POD_REQUIRE(logits && probs && score && cls && level_off && B > 0 && R > 0 && K > 0, "pod_scores: bad args");
   POD_REQUIRE(!logvar || draws > 0, "pod_scores: draws must be positive with logvar");
   LevelTable lt;
@@ -219,7 +221,7 @@ extern "C" __attribute__((visibility("default"))) int pod_scores(const float* lo
   const int64_t total = (int64_t)B * lt.grp_off[n_levels];
   const int grid = (int)((total + 127) / 128 < (int64_t)pod_num_sms() * 16 ? (total + 127) / 128 : (int64_t)pod_num_sms() * 16);
   k_scores<<<grid, 128, 0, (cudaStream_t)stream>>>(logits, logvar, B, R, K, lt, draws, pod_key(seed, POD_STREAM_LOGIT),
-                                                   image0, probs, score, cls);
+                                                   image0, runs, probs, score, cls);
   POD_LAUNCH_CHECK();
   return 0;
 }

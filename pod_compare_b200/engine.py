@@ -225,9 +225,13 @@ class HeadEngine:
         return raw, level_off
 
     # ------------------------------------------------------------------ statistics + post-processing
-    def candidates(self, raw, level_off, anchors, seed, image0):
-        """Q1 means -> scores -> top-k -> decode + covariance."""
+    def candidates(self, raw, level_off, anchors, seed, image0, runs=1):
+        """Q1 means -> scores -> top-k -> decode + covariance.  With runs > 1 every (image, sample) row of
+        `raw` is treated as its own single-sample inference (post-NMS merge modes)."""
         pc = self.pc
+        if runs > 1:
+            raw = {k: (v.reshape((v.shape[0] * v.shape[1], 1) + tuple(v.shape[2:])) if v is not None else None)
+                   for k, v in raw.items()}
         S = raw["logits"].shape[1]
         if S > 1:
             m_logits = ops.sample_mean_q1(raw["logits"])
@@ -242,19 +246,29 @@ class HeadEngine:
                 m_logits, m_deltas = m_logits.contiguous(), m_deltas.contiguous()
                 m_logvar = m_logvar.contiguous() if m_logvar is not None else None
                 m_regvar = m_regvar.contiguous() if m_regvar is not None else None
-        probs, score, cls = ops.scores(m_logits, m_logvar, level_off, pc.cls_var_num_samples, seed, image0)
+        probs, score, cls = ops.scores(m_logits, m_logvar, level_off, pc.cls_var_num_samples, seed, image0, runs=runs)
         cand_idx, cand_cnt, seg = ops.topk_levels(score, level_off, pc.topk, pc.score_thresh)
         cand = ops.decode_cov(m_deltas, m_regvar, raw["deltas"] if S > 1 else None, anchors, probs, score, cls,
-                              cand_idx, cand_cnt, seg, pc.box_num_samples, seed, image0, pc.reg_weights)
+                              cand_idx, cand_cnt, seg, pc.box_num_samples, seed, image0, pc.reg_weights, runs=runs)
         return cand
 
-    def detections(self, cand, fuse_mode, image_hw, out_hw, nms_variant=ops.NMS_AUTO):
+    def detections(self, cand, fuse_mode, image_hw, out_hw, nms_variant=ops.NMS_AUTO, skip_post=False):
         """fuse_mode: 0 standard NMS, 1 BayesOD, 2 anchor statistics."""
         pc = self.pc
         return ops.nms_fuse(cand, int(fuse_mode), pc.nms_thresh, pc.affinity, pc.max_dets, image_hw, out_hw,
-                            nms_variant=nms_variant,
+                            nms_variant=nms_variant, skip_post=skip_post,
                             box_merge=0 if pc.box_merge == "bayesian_inference" else 1,
                             cls_merge=0 if pc.cls_merge == "max_score" else 1)
+
+
+    def merged_detections(self, raw, level_off, anchors, seed, image0, image_hw, out_hw):
+        """Post-NMS merging (reference probabilistic_inference.py:444-481,506-534 and
+        inference_utils.py:165-289): per-run inference + NMS, sequential clustering, final NMS + rescale."""
+        runs = raw["logits"].shape[1]
+        cand = self.candidates(raw, level_off, anchors, seed, image0, runs=runs)
+        per_run = self.detections(cand, 0, image_hw, image_hw, skip_post=True)
+        clusters = ops.cluster_merge(per_run, runs, self.pc.affinity)
+        return cand, per_run, clusters, self.detections(clusters, 0, image_hw, out_hw)
 
 
 def make_anchors(level_hw, sizes, aspect_ratios, strides, offset=0.0, device="cuda"):

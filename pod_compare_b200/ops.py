@@ -10,7 +10,8 @@ import math
 import torch
 
 from . import _cabi
-from ._cabi import POD_OUT_HIDDEN, POD_OUT_RAW, ConvArgs, DecodeArgs, Dropout, NmsArgs, check, int_array, ptr, stream_ptr
+from ._cabi import (POD_OUT_HIDDEN, POD_OUT_RAW, ConvArgs, DecodeArgs, Dropout, MergeArgs, NmsArgs, check, int_array, ptr,
+                    stream_ptr)
 
 _launches = 0
 PROFILE = None      # bench.py sets this to a list: (start_event, end_event, algorithmic FLOPs, tag) per conv launch
@@ -212,8 +213,9 @@ def sample_mean_q1(x):
     return out
 
 
-def scores(logits, logvar, level_off, draws, seed, image0):
-    """logits/logvar (B,R,K) -> probs (B,R,K), score (B,R), cls (B,R) int32."""
+def scores(logits, logvar, level_off, draws, seed, image0, runs=1):
+    """logits/logvar (B,R,K) -> probs (B,R,K), score (B,R), cls (B,R) int32.  With runs > 1 row b is run
+    b % runs of image image0 + b // runs (own noise draws per run)."""
     lib = _cabi.require_device()
     _chk(logits, torch.float32, "logits")
     if logvar is not None:
@@ -223,7 +225,7 @@ def scores(logits, logvar, level_off, draws, seed, image0):
     score = torch.empty((B, R), dtype=torch.float32, device=logits.device)
     cls = torch.empty((B, R), dtype=torch.int32, device=logits.device)
     check(lib.pod_scores(ptr(logits), ptr(logvar), B, R, K, len(level_off) - 1, int_array(level_off), draws, seed, image0,
-                         ptr(probs), ptr(score), ptr(cls), stream_ptr()), "pod_scores")
+                         runs, ptr(probs), ptr(score), ptr(cls), stream_ptr()), "pod_scores")
     _count()
     return probs, score, cls
 
@@ -250,7 +252,7 @@ def topk_levels(score, level_off, topk, thresh):
 
 
 def decode_cov(mean_delta, mean_regvar, sample_delta, anchors, probs, score, cls, cand_idx, cand_cnt, seg, box_draws,
-               seed, image0, reg_weights):
+               seed, image0, reg_weights, runs=1):
     lib = _cabi.require_device()
     B, R, K = probs.shape
     cap = seg[-1]
@@ -277,6 +279,7 @@ def decode_cov(mean_delta, mean_regvar, sample_delta, anchors, probs, score, cls
     seg_arr = int_array(seg)
     a.seg_off_host = seg_arr
     a.box_draws, a.seed, a.image0 = box_draws, int(seed) & 0xFFFFFFFFFFFFFFFF, image0
+    a.runs = runs
     a.wx, a.wy, a.ww, a.wh = [float(v) for v in reg_weights]
     a.out_boxes, a.out_cov = out["boxes"].data_ptr(), out["cov"].data_ptr()
     a.out_scores, a.out_classes = out["scores"].data_ptr(), out["classes"].data_ptr()
@@ -290,7 +293,8 @@ def decode_cov(mean_delta, mean_regvar, sample_delta, anchors, probs, score, cls
 NMS_VANILLA, NMS_TRICK, NMS_AUTO = 0, 1, 2
 
 
-def nms_fuse(cand, mode, nms_thresh, affinity, max_dets, in_hw, out_hw, nms_variant=NMS_AUTO, box_merge=0, cls_merge=0):
+def nms_fuse(cand, mode, nms_thresh, affinity, max_dets, in_hw, out_hw, nms_variant=NMS_AUTO, box_merge=0, cls_merge=0,
+             skip_post=False):
     """cand: dict with boxes (B,cap,4), cov (B,cap,4,4), scores, classes (int32), probs, count, has_cov."""
     lib = _cabi.require_device()
     B, cap, K = cand["probs"].shape
@@ -323,6 +327,37 @@ def nms_fuse(cand, mode, nms_thresh, affinity, max_dets, in_hw, out_hw, nms_vari
     a.det_probs, a.det_count = out["probs"].data_ptr(), out["count"].data_ptr()
     a.keep, a.keep_count = out["keep"].data_ptr(), out["keep_count"].data_ptr()
     a.det_src = out["src"].data_ptr()
+    a.skip_post = int(bool(skip_post))
     check(lib.pod_nms_fuse(C.byref(a), stream_ptr()), "pod_nms_fuse")
+    _count()
+    return out
+
+
+def cluster_merge(det, runs, affinity):
+    """Per-run detections (B*runs rows, from nms_fuse(skip_post=True)) -> clustered candidate set per image
+    (reference general_black_box_ensembles_post_processing up to its final NMS)."""
+    lib = _cabi.require_device()
+    BR, D, K = det["probs"].shape
+    assert BR % runs == 0
+    B = BR // runs
+    cap = runs * D
+    dev = det["probs"].device
+    out = {
+        "boxes": torch.zeros((B, cap, 4), dtype=torch.float32, device=dev),
+        "cov": torch.zeros((B, cap, 4, 4), dtype=torch.float32, device=dev),
+        "scores": torch.zeros((B, cap), dtype=torch.float32, device=dev),
+        "classes": torch.zeros((B, cap), dtype=torch.int32, device=dev),
+        "probs": torch.zeros((B, cap, K), dtype=torch.float32, device=dev),
+        "count": torch.zeros((B,), dtype=torch.int32, device=dev),
+        "has_cov": True,
+    }
+    a = MergeArgs()
+    a.det_boxes, a.det_cov = det["boxes"].data_ptr(), det["cov"].data_ptr()
+    a.det_probs, a.det_classes, a.det_count = det["probs"].data_ptr(), det["classes"].data_ptr(), det["count"].data_ptr()
+    a.B, a.runs, a.max_dets, a.K = B, runs, D, K
+    a.affinity = float(affinity)
+    a.out_boxes, a.out_cov, a.out_scores = out["boxes"].data_ptr(), out["cov"].data_ptr(), out["scores"].data_ptr()
+    a.out_classes, a.out_probs, a.out_count = out["classes"].data_ptr(), out["probs"].data_ptr(), out["count"].data_ptr()
+    check(lib.pod_cluster_merge(C.byref(a), stream_ptr()), "pod_cluster_merge")
     _count()
     return out

@@ -167,10 +167,8 @@ class ProbabilisticPredictor:
             raise _cabi.PodError("no weights loaded: call load_weight_sets(state_dicts) first")
         mode = self.inference_mode
         pi = self.cfg.PROBABILISTIC_INFERENCE
-        if mode == 'mc_dropout_ensembles' and pi.ENSEMBLES_DROPOUT.BOX_MERGE_MODE != 'pre_nms':
-            raise NotImplementedError("post_nms MC-dropout merging is outside the rebuilt path (SURVEY 8f rank 1)")
-        if mode == 'ensembles' and pi.ENSEMBLES.BOX_MERGE_MODE != 'pre_nms':
-            raise NotImplementedError("post_nms ensemble merging is outside the rebuilt path (SURVEY 8f rank 1)")
+        post_nms = ((mode == 'mc_dropout_ensembles' and pi.ENSEMBLES_DROPOUT.BOX_MERGE_MODE != 'pre_nms') or
+                    (mode == 'ensembles' and pi.ENSEMBLES.BOX_MERGE_MODE != 'pre_nms'))
         if mode not in SUPPORTED_PRE_NMS_MODES:
             raise ValueError('Invalid inference mode {}.'.format(mode))
         out_hw = tuple(out_hw) if out_hw is not None else tuple(image_hw)
@@ -189,8 +187,11 @@ class ProbabilisticPredictor:
             raw, level_off = eng.head_mc(feats, self.num_mc_dropout_runs, seed, image0)
         else:
             raw, level_off = eng.head_eval(feats, members=[0])
-        cand = eng.candidates(raw, level_off, anchors, seed, image0)
-        det = eng.detections(cand, {'bayes_od': 1, 'anchor_statistics': 2}.get(mode, 0), image_hw, out_hw)
+        if post_nms:
+            cand, _, _, det = eng.merged_detections(raw, level_off, anchors, seed, image0, image_hw, out_hw)
+        else:
+            cand = eng.candidates(raw, level_off, anchors, seed, image0)
+            det = eng.detections(cand, {'bayes_od': 1, 'anchor_statistics': 2}.get(mode, 0), image_hw, out_hw)
         res = self._to_instances(det, out_hw)
         if return_raw or return_candidates:
             return res, (raw if return_raw else None), cand, det
