@@ -31,29 +31,53 @@ N_MC = 30
 TOWER_FLOP_PER_LOC = 2 * 9 * 256 * 256          # 1,179,648 FLOP per location per tower conv
 
 
-def build_cfg(n_mc):
-    from pod_compare_b200.config import get_cfg
-    cfg = get_cfg()
-    cfg.MODEL.RETINANET.NUM_CLASSES = 7
-    cfg.merge_from_list([
-        "MODEL.PROBABILISTIC_MODELING.DROPOUT_RATE", 0.2,
-        "MODEL.PROBABILISTIC_MODELING.CLS_VAR_LOSS.NAME", "loss_attenuation",
+_VAR = ["MODEL.PROBABILISTIC_MODELING.CLS_VAR_LOSS.NAME", "loss_attenuation",
         "MODEL.PROBABILISTIC_MODELING.CLS_VAR_LOSS.NUM_SAMPLES", 10,
         "MODEL.PROBABILISTIC_MODELING.BBOX_COV_LOSS.NAME", "negative_log_likelihood",
-        "MODEL.PROBABILISTIC_MODELING.BBOX_COV_LOSS.COVARIANCE_TYPE", "diagonal",
-        "PROBABILISTIC_INFERENCE.INFERENCE_MODE", "mc_dropout_ensembles",
-        "PROBABILISTIC_INFERENCE.AFFINITY_THRESHOLD", 0.9,
-        "PROBABILISTIC_INFERENCE.MC_DROPOUT.ENABLE", True,
-        "PROBABILISTIC_INFERENCE.MC_DROPOUT.NUM_RUNS", n_mc,
-        "PROBABILISTIC_INFERENCE.ENSEMBLES_DROPOUT.BOX_MERGE_MODE", "pre_nms"])
+        "MODEL.PROBABILISTIC_MODELING.BBOX_COV_LOSS.COVARIANCE_TYPE", "diagonal"]
+# BASELINE.json configs (index) -> (description, cfg options, uses MC-dropout, ensemble members)
+WORKLOADS = {
+    "mc_pre": ("BASELINE configs[2]: reg_cls_var_dropout head, mc_dropout_ensembles pre_nms",
+               _VAR + ["MODEL.PROBABILISTIC_MODELING.DROPOUT_RATE", 0.2,
+                       "PROBABILISTIC_INFERENCE.INFERENCE_MODE", "mc_dropout_ensembles",
+                       "PROBABILISTIC_INFERENCE.ENSEMBLES_DROPOUT.BOX_MERGE_MODE", "pre_nms"], True, 1),
+    "mc_post": ("reg_cls_var_dropout head, mc_dropout_ensembles post_nms",
+                _VAR + ["MODEL.PROBABILISTIC_MODELING.DROPOUT_RATE", 0.2,
+                        "PROBABILISTIC_INFERENCE.INFERENCE_MODE", "mc_dropout_ensembles",
+                        "PROBABILISTIC_INFERENCE.ENSEMBLES_DROPOUT.BOX_MERGE_MODE", "post_nms"], True, 1),
+    "bayes_od_mc": ("BASELINE configs[3]: reg_cls_var_dropout head, bayes_od (max_score / bayesian_inference)",
+                    _VAR + ["MODEL.PROBABILISTIC_MODELING.DROPOUT_RATE", 0.2,
+                            "PROBABILISTIC_INFERENCE.INFERENCE_MODE", "bayes_od",
+                            "PROBABILISTIC_INFERENCE.BAYES_OD.CLS_MERGE_MODE", "max_score",
+                            "PROBABILISTIC_INFERENCE.BAYES_OD.BOX_MERGE_MODE", "bayesian_inference"], True, 1),
+    "loss_att": ("BASELINE configs[1]: reg_cls_var head (loss attenuation), standard_nms, single forward",
+                 _VAR + ["PROBABILISTIC_INFERENCE.INFERENCE_MODE", "standard_nms"], False, 1),
+    "baseline": ("BASELINE configs[0]: baseline RetinaNet head, standard_nms, single forward",
+                 ["PROBABILISTIC_INFERENCE.INFERENCE_MODE", "standard_nms"], False, 1),
+    "ensembles5": ("BASELINE configs[4]: reg_cls_var head, 5-member ensembles pre_nms",
+                   _VAR + ["PROBABILISTIC_INFERENCE.INFERENCE_MODE", "ensembles",
+                           "PROBABILISTIC_INFERENCE.ENSEMBLES.BOX_MERGE_MODE", "pre_nms"], False, 5),
+}
+
+
+def build_cfg(n_mc, workload="mc_pre"):
+    from pod_compare_b200.config import get_cfg
+    desc, opts, mc, members = WORKLOADS[workload]
+    cfg = get_cfg()
+    cfg.MODEL.RETINANET.NUM_CLASSES = 7
+    cfg.merge_from_list(list(opts) + ["PROBABILISTIC_INFERENCE.AFFINITY_THRESHOLD", 0.9])
+    if mc:
+        cfg.merge_from_list(["PROBABILISTIC_INFERENCE.MC_DROPOUT.ENABLE", True,
+                             "PROBABILISTIC_INFERENCE.MC_DROPOUT.NUM_RUNS", n_mc])
     cfg.SEED = 0
     cfg.freeze()
     return cfg
 
 
 def workload_config(args, world):
-    return {"workload": "BASELINE configs[2]: reg_cls_var_dropout head, mc_dropout_ensembles pre_nms, N=%d, "
-                        "batch %d per GPU, 1280x720 (FPN features in, detections out)" % (args.n_mc, args.batch),
+    desc, _, mc, members = WORKLOADS[args.workload]
+    return {"workload": "%s, %s, batch %d per GPU, 1280x720 (FPN features in, detections out)"
+                        % (desc, ("N=%d" % args.n_mc) if mc else ("E=%d" % members if members > 1 else "N=1"), args.batch),
             "global_batch": args.batch * world, "batch_per_gpu": args.batch, "mc_samples": args.n_mc,
             "image": "%dx%d" % (WIDTH, HEIGHT), "chunk_images": args.chunk,
             "parallelism": "image-sharded dp%d + NCCL all-gather of detections" % world,
@@ -166,6 +190,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=16, help="images processed per head pass (memory bound)")
     ap.add_argument("--n-mc", type=int, default=N_MC)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="mc_pre", choices=sorted(WORKLOADS),
+                    help="mc_pre = the headline metric (BASELINE configs[2]); the others are side measurements")
     ap.add_argument("--kblock", type=int, default=0)
     ap.add_argument("--pair", type=int, default=-1, help="1/0: force CTA-pair (cta_group::2) / single-CTA tower convs")
     ap.add_argument("--chunk-taps", type=int, default=0, help="taps per accumulation chunk (1, 3, 9)")
@@ -191,9 +217,13 @@ def main():
     if args.chunk_taps:
         ops.set_conv_chunk_taps(args.chunk_taps)
 
-    cfg = build_cfg(args.n_mc)
+    cfg = build_cfg(args.n_mc, args.workload)
     pred = build_predictor(cfg)
-    pred.load_weight_sets(S.make_head_state_dict(0, num_classes=7, use_dropout=True, cls_var=True, bbox_cov=True))
+    m = pred.model
+    members = WORKLOADS[args.workload][3]
+    sds = [S.make_head_state_dict(1000 * e, num_classes=7, use_dropout=m.use_dropout, cls_var=m.compute_cls_var,
+                                  bbox_cov=m.compute_bbox_cov) for e in range(members)]
+    pred.load_weight_sets(sds if members > 1 else sds[0])
     B = args.batch
     # synthetic FPN features of this rank's images (weak scaling: B images per GPU)
     img0 = rank * B
@@ -309,7 +339,9 @@ def main():
             "config": workload_config(args, world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": launches, "roofline": roof}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if args.workload != "mc_pre":
+        line["metric"] = "images/sec, side workload (not the BASELINE headline)"
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "mc_pre":
         v, cores, desc = cpu_path_rate(args.n_mc, samples_timed=2)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
     if rank == 0:

@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(NT) k_nms_fuse(pod_nms_args a, float sx, float
   __shared__ BoxA s_kept[MAX_DETS];
   __shared__ int s_kept_idx[MAX_DETS];
   __shared__ unsigned char s_alive[NT];
-  __shared__ int s_first, s_nkept;
+  __shared__ int s_first;
+  __shared__ int s_nkept;
   __shared__ float s_red[NT / 32];
   __shared__ float s_out_box[MAX_DETS][4];
   __shared__ float s_out_score[MAX_DETS];
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(NT) k_nms_fuse(pod_nms_args a, float sx, float
       __syncthreads();
       if (s_alive[tid] && tid >= cursor) atomicMin(&s_first, tid);
       __syncthreads();
-      const int first = s_first;
+      const int first = *reinterpret_cast<volatile int*>(&s_first);   // scalar load: never fused with s_nkept
       if (first >= NT) break;
       if (tid == first) {
         const int slot = s_nkept;

@@ -119,6 +119,13 @@ class ProbabilisticPredictor:
         self._engine = HeadEngine(self.path_config(), self.weight_sets, self.device)
         return self
 
+    def load_backbone(self, state_dict):
+        """Install the torch ResNet-50-FPN feature extractor (detectron2 key names, backbone.py) so that
+        `predictor(input_im)` accepts raw images."""
+        from .backbone import ResNetFPNBackbone
+        self.backbone = ResNetFPNBackbone(state_dict, self.cfg.MODEL.PIXEL_MEAN, self.cfg.MODEL.PIXEL_STD, self.device)
+        return self
+
     def _anchors(self, level_hw):
         key = tuple(level_hw)
         if key not in self._anchor_cache:

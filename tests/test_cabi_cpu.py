@@ -96,3 +96,17 @@ def test_reference_config_yaml_surface():
         assert c.PROBABILISTIC_INFERENCE.BAYES_OD.CLS_MERGE_MODE == "max_score"
         assert abs(c.MODEL.ANCHOR_GENERATOR.SIZES[0][1] - 32 * 2 ** (1 / 3)) < 1e-9
         assert c.is_frozen()
+
+
+def test_backbone_shapes_and_keys_cpu():
+    """The upstream ResNet-50-FPN restatement (library torch ops): detectron2 key coverage and the
+    P3..P7 geometry the head path expects (strides 8..128 of the 128-padded image)."""
+    from pod_compare_b200 import backbone as BB
+    sd = BB.random_state_dict(0)
+    assert sorted(sd) == sorted(BB.expected_keys())
+    net = BB.ResNetFPNBackbone(sd, device="cpu")
+    img = torch.randint(0, 256, (3, 100, 190), dtype=torch.uint8)
+    feats = net([img, img])
+    assert [tuple(f.shape) for f in feats] == [(2, 256, 16, 32), (2, 256, 8, 16), (2, 256, 4, 8), (2, 256, 2, 4), (2, 256, 1, 2)]
+    assert all(torch.isfinite(f).all() for f in feats)
+    assert torch.equal(feats[0][0], feats[0][1])

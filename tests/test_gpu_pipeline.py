@@ -452,3 +452,20 @@ def test_full_size_path_properties_and_parity():
     one = {k: (v[:1] if isinstance(v, torch.Tensor) else v) for k, v in cand.items()}
     one_det = {k: (v[:1] if isinstance(v, torch.Tensor) else v) for k, v in det.items()}
     _compare_path(res[0], one, one_det, ref_final, ref_cand, ref_det, pp, False)
+
+
+def test_predictor_from_raw_images_with_backbone():
+    """predictor(input_im) from a raw image through the torch ResNet-50-FPN backbone (upstream of the
+    rebuilt path) equals infer_from_features on the backbone's maps."""
+    from pod_compare_b200 import backbone as BB
+    name = "regclsvar_std"
+    cfg, pp, sds, _ = _oracle_case(name)
+    pred = build_predictor(cfg)
+    pred.load_weight_sets(sds[0])
+    pred.load_backbone(BB.random_state_dict(1))
+    img = S.make_image(0, 0, 96, 160)
+    inst = pred([{"image": img, "height": 96, "width": 160, "image_id": 0}])
+    feats = pred.backbone([img])
+    assert [tuple(f.shape[-2:]) for f in feats] == [(16, 32), (8, 16), (4, 8), (2, 4), (1, 2)]
+    ref = pred.infer_from_features(feats, (96, 160), (96, 160), image0=0)[0]
+    assert len(inst) == len(ref) and torch.equal(inst.pred_boxes.tensor, ref.pred_boxes.tensor)
