@@ -49,6 +49,8 @@ CASES = {
     "ensembles_post_e3": (_VAR + _mode("ensembles") + ["PROBABILISTIC_INFERENCE.ENSEMBLES.RANDOM_SEED_NUMS", [0, 1000, 2000],
                           "PROBABILISTIC_INFERENCE.ENSEMBLES.BOX_MERGE_MODE", "post_nms"], "ensembles", 1, [0, 1000, 2000],
                           (96, 160), (96, 160), 23, 12),
+    "coco80_std": (_VAR + _mode("standard_nms") + ["MODEL.RETINANET.NUM_CLASSES", 80], "standard_nms", 1, [0],
+                   (64, 64), (64, 64), 24, 13),
     "fullcov_mc_n3": (_VAR + _FULL + _DROP + _mode("mc_dropout_ensembles") + _mc(3), "mc_dropout_ensembles", 3, [3000],
                       (96, 160), (96, 160), 19, 8),
 }
@@ -57,7 +59,7 @@ CASES = {
 def build_cfg(name):
     opts = CASES[name][0]
     cfg = get_cfg()
-    cfg.MODEL.RETINANET.NUM_CLASSES = 7        # BDD (reference Base-BDD-RetinaNet.yaml:12)
+    cfg.MODEL.RETINANET.NUM_CLASSES = 7        # BDD (reference Base-BDD-RetinaNet.yaml:12) unless the case overrides it
     cfg.merge_from_list(list(opts))
     cfg.MODEL.DEVICE = "cpu"
     cfg.freeze()

@@ -44,6 +44,8 @@ class PackedConv:
     w_scale: float
     cout: int
     cout_pad: int
+    col0: int = 0          # first output channel of this block (convs wider than 256 channels are split)
+    total_cout: int = 0    # output channels of the whole convolution
 
 
 def pack_conv(weight, bias, device):
@@ -54,7 +56,19 @@ def pack_conv(weight, bias, device):
     hi, lo = ops.pack_conv_weight(w, cout_pad, scale)
     b = torch.zeros((cout_pad,), dtype=torch.float32, device=device)
     b[:cout] = bias.detach().to(device=device, dtype=torch.float32)
-    return PackedConv(hi, lo, b, scale, cout, cout_pad)
+    return PackedConv(hi, lo, b, scale, cout, cout_pad, 0, cout)
+
+
+def pack_conv_blocks(weight, bias, device, block=256):
+    """Output convolution of any width (e.g. A*K = 720 channels for 80 classes) as column blocks of at most
+    256 output channels, one tcgen05 launch each, all writing into the same permuted output rows."""
+    cout = weight.shape[0]
+    blocks = []
+    for c0 in range(0, cout, block):
+        pcv = pack_conv(weight[c0:c0 + block], bias[c0:c0 + block], device)
+        pcv.col0, pcv.total_cout = c0, cout
+        blocks.append(pcv)
+    return blocks
 
 
 class HeadWeights:
@@ -71,10 +85,10 @@ class HeadWeights:
                                                     sd["head.cls_subnet.%d.bias" % (i * step)], device))
             self.towers[TOWER_BOX].append(pack_conv(sd["head.bbox_subnet.%d.weight" % (i * step)],
                                                     sd["head.bbox_subnet.%d.bias" % (i * step)], device))
-        self.cls_score = pack_conv(sd["head.cls_score.weight"], sd["head.cls_score.bias"], device)
-        self.bbox_pred = pack_conv(sd["head.bbox_pred.weight"], sd["head.bbox_pred.bias"], device)
-        self.cls_var = pack_conv(sd["head.cls_var.weight"], sd["head.cls_var.bias"], device) if cls_var else None
-        self.bbox_cov = pack_conv(sd["head.bbox_cov.weight"], sd["head.bbox_cov.bias"], device) if bbox_cov else None
+        self.cls_score = pack_conv_blocks(sd["head.cls_score.weight"], sd["head.cls_score.bias"], device)
+        self.bbox_pred = pack_conv_blocks(sd["head.bbox_pred.weight"], sd["head.bbox_pred.bias"], device)
+        self.cls_var = pack_conv_blocks(sd["head.cls_var.weight"], sd["head.cls_var.bias"], device) if cls_var else None
+        self.bbox_cov = pack_conv_blocks(sd["head.bbox_cov.weight"], sd["head.bbox_cov.bias"], device) if bbox_cov else None
 
 
 @dataclass
@@ -120,11 +134,12 @@ class HeadEngine:
         ops.conv3x3_tc(src[0], src[1], ACT_SCALE, NB, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, pcv.cout,
                        pcv.cout_pad, POD_OUT_HIDDEN, True, out_hi=dst[0], out_lo=dst[1], out_scale=ACT_SCALE, drop=drop)
 
-    def _conv_out(self, src, NB, H, W, pcv, out, out_offset, out_map_stride, in_map_stride=None, in_offset=0):
-        ops.conv3x3_tc(src[0], src[1], ACT_SCALE, NB, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, pcv.cout,
-                       pcv.cout_pad, POD_OUT_RAW, False, out_f32=out, out_offset=out_offset,
-                       out_map_stride=out_map_stride, out_pixel_stride=pcv.cout,
-                       in_map_stride=in_map_stride, in_offset=in_offset)
+    def _conv_out(self, src, NB, H, W, blocks, out, out_offset, out_map_stride, in_map_stride=None, in_offset=0):
+        for pcv in blocks:
+            ops.conv3x3_tc(src[0], src[1], ACT_SCALE, NB, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, pcv.cout,
+                           pcv.cout_pad, POD_OUT_RAW, False, out_f32=out, out_offset=out_offset + pcv.col0,
+                           out_map_stride=out_map_stride, out_pixel_stride=pcv.total_cout,
+                           in_map_stride=in_map_stride, in_offset=in_offset)
 
     def head_mc(self, feats, n_mc, seed, image0):
         """MC-dropout head loop: feats = list over levels of (B,256,H,W) fp32.
@@ -171,12 +186,12 @@ class HeadEngine:
                 # output convs: pass-0 maps feed the mean head, pass-1 maps the variance head (Q2)
                 mean_pc, var_pc = (w.cls_score, w.cls_var) if tower == TOWER_CLS else (w.bbox_pred, w.bbox_cov)
                 mean_out = raw["logits"] if tower == TOWER_CLS else raw["deltas"]
-                D = mean_pc.cout // A
+                D = mean_pc[0].total_cout // A
                 self._conv_out(act[cur], B * n_mc, H, W, mean_pc, mean_out, level_off[lvl] * D, R * D,
                                in_map_stride=t_passes * HW * 256, in_offset=0)
                 if has_var:
                     var_out = raw["logvar"] if tower == TOWER_CLS else raw["regvar"]
-                    Dv = var_pc.cout // A
+                    Dv = var_pc[0].total_cout // A
                     self._conv_out(act[cur], B * n_mc, H, W, var_pc, var_out, level_off[lvl] * Dv, R * Dv,
                                    in_map_stride=2 * HW * 256, in_offset=HW * 256)
         return raw, level_off
@@ -216,11 +231,11 @@ class HeadEngine:
                         cur ^= 1
                     mean_pc, var_pc = (w.cls_score, w.cls_var) if tower == TOWER_CLS else (w.bbox_pred, w.bbox_cov)
                     mean_out = raw["logits"] if tower == TOWER_CLS else raw["deltas"]
-                    D = mean_pc.cout // A
+                    D = mean_pc[0].total_cout // A
                     self._conv_out(src, B, H, W, mean_pc, mean_out, (e * R + level_off[lvl]) * D, E * R * D)
                     if var_pc is not None:
                         var_out = raw["logvar"] if tower == TOWER_CLS else raw["regvar"]
-                        Dv = var_pc.cout // A
+                        Dv = var_pc[0].total_cout // A
                         self._conv_out(src, B, H, W, var_pc, var_out, (e * R + level_off[lvl]) * Dv, E * R * Dv)
         return raw, level_off
 
