@@ -13,10 +13,22 @@ yacs/detectron2 are not available here, so `CfgNode` is a small attribute dict w
 the subset of the yacs API the reference touches (clone, defrost, freeze,
 merge_from_file, merge_from_list, item access).
 """
+import ast
 import copy
 import os
 
 import yaml
+
+
+def _decode(value):
+    """yacs `_decode_cfg_value`: strings that are Python literals (the reference YAMLs write tuples as
+    `("bdd_train",)` or `(60000, 80000)`) become the literal; anything else stays a string."""
+    if not isinstance(value, str):
+        return value
+    try:
+        return ast.literal_eval(value)
+    except (ValueError, SyntaxError):
+        return value
 
 
 class CfgNode(dict):
@@ -96,6 +108,7 @@ def _merge(dst, src, path):
                 raise KeyError("Config key {} is not a node".format(".".join(path + [k])))
             _merge(dst[k], v, path + [k])
         else:
+            v = _decode(v)
             if isinstance(v, (list, tuple)):
                 v = type(dst.get(k, v))(v) if isinstance(dst.get(k, None), (list, tuple)) else v
             dst[k] = v

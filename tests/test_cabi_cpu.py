@@ -110,3 +110,21 @@ def test_backbone_shapes_and_keys_cpu():
     assert [tuple(f.shape) for f in feats] == [(2, 256, 16, 32), (2, 256, 8, 16), (2, 256, 4, 8), (2, 256, 2, 4), (2, 256, 1, 2)]
     assert all(torch.isfinite(f).all() for f in feats)
     assert torch.equal(feats[0][0], feats[0][1])
+
+
+def test_shipped_configs_cover_the_reference_plugin_surface():
+    """The YAMLs shipped in pod_compare_b200/configs (5 model variants x 8 inference modes) resolve, and --
+    where the reference tree is present -- to exactly the configuration the reference's own files give."""
+    import glob
+    from pod_compare_b200.config import setup_config
+    d = os.path.join(ROOT, "pod_compare_b200", "configs")
+    models = sorted(glob.glob(os.path.join(d, "BDD-Detection", "retinanet", "retinanet*.yaml")))
+    modes = sorted(glob.glob(os.path.join(d, "Inference", "*.yaml")))
+    assert len(models) == 4 and len(modes) == 8
+    ref = "/root/reference/src/configs"
+    for m in models:
+        for i in modes:
+            cfg = setup_config(m, i)
+            assert cfg.MODEL.META_ARCHITECTURE == "ProbabilisticRetinaNet" and cfg.MODEL.RETINANET.NUM_CLASSES == 7
+            if os.path.isdir(ref):
+                assert cfg == setup_config(m.replace(d, ref), i.replace(d, ref)), (m, i)
