@@ -245,3 +245,83 @@ def test_topk_ties_and_full_range():
         order = order[sc[order] > 0.05]
         assert int(cand_cnt[0, l]) == order.numel()
         assert torch.equal(cand_idx[0, seg[l]:seg[l] + order.numel()].long(), order + off[l])
+
+
+# ------------------------------------------------------------------------------------------ randomized selection tests
+def _random_candidates(seed, M, K=7, tie_scores=False, img=(720, 1280)):
+    g = torch.Generator().manual_seed(seed)
+    n_gt = max(1, M // 12)
+    centers = torch.rand((n_gt, 2), generator=g) * torch.tensor([img[1] * 0.8, img[0] * 0.8])
+    sizes = torch.rand((n_gt, 2), generator=g) * 250 + 20
+    which = torch.randint(0, n_gt, (M,), generator=g)
+    jit = torch.randn((M, 4), generator=g) * torch.rand((M, 1), generator=g) * 12
+    x1y1 = centers[which] + jit[:, :2]
+    boxes = torch.cat([x1y1, x1y1 + sizes[which] + jit[:, 2:]], 1).float()
+    boxes[:: max(M // 7, 1), 2:] = boxes[:: max(M // 7, 1), :2]              # some zero-area boxes
+    classes = torch.randint(0, K, (M,), generator=g)
+    scores = torch.rand((M,), generator=g) * 0.9 + 0.05
+    if tie_scores:
+        scores = (scores * 20).round() / 20 + 0.01                           # many exactly equal scores
+    probs = torch.rand((M, K), generator=g) * 0.04
+    probs[torch.arange(M), classes] = scores
+    A = torch.randn((M, 4, 4), generator=g)
+    cov = A @ A.transpose(1, 2) + torch.eye(4)[None]
+    return O.Candidates(boxes, cov.float(), scores.float(), classes, probs.float(), np.arange(M), [M])
+
+
+@pytest.mark.parametrize("M", [1, 2, 33, 257, 999, 1000, 1001, 2500, 5000])
+@pytest.mark.parametrize("ties", [False, True])
+def test_nms_survivors_bit_exact_random(M, ties):
+    """NMS survivor indices against the scalar restatement of torchvision's CPU loop (stable order, lower
+    index first on equal scores) and against the installed torchvision op when scores are distinct; both
+    batched_nms variants; zero-area boxes included."""
+    c = _random_candidates(1000 + M, M, tie_scores=ties)
+    pp = O.PathParams()
+    cd = G.cand_to_dict(c)
+    for variant in (ops.NMS_AUTO, ops.NMS_VANILLA, ops.NMS_TRICK):
+        det = ops.nms_fuse(cd, 0, 0.5, 0.9, 100, (720, 1280), (720, 1280), nms_variant=variant)
+        n = int(det["keep_count"][0])
+        got = det["keep"][0, :n].cpu().numpy().astype(np.int64)
+        auto_is_vanilla = 4 * M > 4000
+        if variant == ops.NMS_AUTO or (variant == ops.NMS_VANILLA) == auto_is_vanilla:
+            ref = O.standard_nms_post(c, pp, (720, 1280), nms_impl="loop").keep.numpy()
+            assert np.array_equal(got, ref), (M, ties, variant)
+            if not ties:
+                ref_tv = O.standard_nms_post(c, pp, (720, 1280), nms_impl="torchvision").keep.numpy()
+                assert np.array_equal(got, ref_tv), (M, variant)
+        else:
+            # the other torchvision variant on the same boxes: restate it directly
+            b = c.boxes.float()
+            if variant == ops.NMS_TRICK:
+                off = c.classes.to(b) * (b.max() + torch.tensor(1).to(b))
+                keep = O.nms_loop(b + off[:, None], c.scores, 0.5)[:100].numpy()
+            else:
+                mask = torch.zeros_like(c.scores, dtype=torch.bool)
+                for k in torch.unique(c.classes):
+                    cur = torch.where(c.classes == k)[0]
+                    mask[cur[O.nms_loop(b[cur], c.scores[cur], 0.5)]] = True
+                kept = torch.where(mask)[0]
+                keep = kept[torch.sort(c.scores[kept], descending=True, stable=True)[1]][:100].numpy()
+            assert np.array_equal(got, keep), (M, ties, variant)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_topk_random_levels_with_ties(seed):
+    g = torch.Generator().manual_seed(seed)
+    sizes = [int(x) for x in torch.randint(1, 6000, (5,), generator=g)]
+    off = [0]
+    for s_ in sizes:
+        off.append(off[-1] + s_)
+    B = 3
+    score = torch.rand((B, off[-1]), generator=g)
+    score = torch.where(torch.rand(score.shape, generator=g) < 0.5, (score * 50).round() / 50, score)   # heavy ties
+    for topk, thr in ((1000, 0.05), (7, 0.5), (1024, 0.0)):
+        cand_idx, cand_cnt, seg = ops.topk_levels(score.cuda(), off, topk, thr)
+        cand_idx, cand_cnt = cand_idx.cpu(), cand_cnt.cpu()
+        for b in range(B):
+            for l in range(5):
+                sc = score[b, off[l]:off[l + 1]]
+                order = torch.sort(sc, descending=True, stable=True)[1][: min(topk, sc.shape[0])]
+                order = order[sc[order] > thr]
+                assert int(cand_cnt[b, l]) == order.numel(), (seed, topk, b, l)
+                assert torch.equal(cand_idx[b, seg[l]:seg[l] + order.numel()].long(), order + off[l])
