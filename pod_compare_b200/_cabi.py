@@ -77,6 +77,15 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
+    # (re)build in-tree when the sources changed or the library is absent and nvcc is available; the
+    # check is a hash of csrc/ and costs nothing when the library is current
+    try:
+        from . import build as _build
+        _build.build()
+    except Exception as e:  # noqa: BLE001
+        if not os.path.exists(LIB_PATH):
+            raise PodError("libpodb200.so is missing (%s) and could not be built (%s): run `python -m "
+                           "pod_compare_b200.build` -- there is no CPU or PyTorch fallback for this path" % (LIB_PATH, e))
     if not os.path.exists(LIB_PATH):
         raise PodError("libpodb200.so is missing (%s): run `python -m pod_compare_b200.build` -- there is no "
                        "CPU or PyTorch fallback for this path" % LIB_PATH)

@@ -37,12 +37,31 @@ def nvcc_path():
     return "nvcc"
 
 
+def _current(dig):
+    if os.path.exists(OUT) and os.path.exists(STAMP):
+        with open(STAMP) as f:
+            return f.read().strip() == dig
+    return False
+
+
 def build(force=False, verbose=False):
     dig = _digest()
-    if not force and os.path.exists(OUT) and os.path.exists(STAMP):
-        with open(STAMP) as f:
-            if f.read().strip() == dig:
-                return OUT
+    if not force and _current(dig):
+        return OUT
+    # one builder at a time (torchrun starts several ranks at once)
+    import fcntl
+    lock = open(os.path.join(CSRC, ".build_lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and _current(dig):
+            return OUT
+        return _build_locked(dig, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(dig, verbose):
     objs = []
     procs = []
     for src in SOURCES:
