@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--kblock", type=int, default=0)
     ap.add_argument("--pair", type=int, default=-1, help="1/0: force CTA-pair (cta_group::2) / single-CTA tower convs")
     ap.add_argument("--chunk-taps", type=int, default=0, help="taps per accumulation chunk (1, 3, 9)")
+    ap.add_argument("--chunk-kblocks", type=int, default=0, help="K-blocks per accumulation chunk (overrides --chunk-taps)")
     args = ap.parse_args()
 
     from pod_compare_b200 import distributed as D
@@ -216,6 +217,8 @@ def main():
         ops.set_conv_pair(args.pair)
     if args.chunk_taps:
         ops.set_conv_chunk_taps(args.chunk_taps)
+    if args.chunk_kblocks:
+        ops.set_conv_chunk_kblocks(args.chunk_kblocks)
 
     cfg = build_cfg(args.n_mc, args.workload)
     pred = build_predictor(cfg)

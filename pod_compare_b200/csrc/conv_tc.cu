@@ -790,6 +790,13 @@ static int dispatch_bn(const Params& P, cudaStream_t st) {
 
 static int g_tc_bk = 64;      // K-block (channels per pipeline stage): 64 -> SWIZZLE_128B (default), 32 -> SWIZZLE_64B
 static int g_tc_taps = 1;     // taps per accumulation chunk (1, 3 or 9)
+static int g_tc_chunk_kb = 0; // if > 0: K-blocks per accumulation chunk (must divide 9*Cin/K-block); overrides taps
+
+extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_chunk_kblocks(int kb) {
+  POD_REQUIRE(kb >= 0, "pod_conv3x3_tc_set_chunk_kblocks: must be >= 0");
+  g_tc_chunk_kb = kb;
+  return 0;
+}
 
 extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_pair(int on) {
   tc::g_tc_pair = on ? 1 : 0;
@@ -838,6 +845,7 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   P.Cout = a->Cout; P.Cout_pad = a->Cout_pad;
   P.relu = a->relu;
   P.kb_per_chunk = g_tc_taps * (a->Cin / BK);
+  if (g_tc_chunk_kb > 0 && (9 * (a->Cin / BK)) % g_tc_chunk_kb == 0) P.kb_per_chunk = g_tc_chunk_kb;
   P.dbg_skip_ld = getenv("POD_TC_DEBUG_SKIP_LD") ? 1 : 0;
   P.acc_scale = 1.0f / (a->in_scale * a->w_scale);
   P.out_scale = a->out_scale;

@@ -181,6 +181,10 @@ def set_conv_pair(on):
     check(_cabi.load_library().pod_conv3x3_tc_set_pair(int(bool(on))), "pod_conv3x3_tc_set_pair")
 
 
+def set_conv_chunk_kblocks(kb):
+    check(_cabi.load_library().pod_conv3x3_tc_set_chunk_kblocks(int(kb)), "pod_conv3x3_tc_set_chunk_kblocks")
+
+
 def set_conv_chunk_taps(taps):
     check(_cabi.load_library().pod_conv3x3_tc_set_chunk_taps(int(taps)), "pod_conv3x3_tc_set_chunk_taps")
 

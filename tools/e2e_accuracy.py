@@ -30,8 +30,12 @@ print("oracle: %.1f s, %d candidates, %d detections" % (time.time() - t0, ref_ca
 pred = build_predictor(cfg)
 pred.load_weight_sets(sd)
 ids_ref = {int(a): i for i, a in enumerate(ref_cand.anchor_ids)}
-for taps in (1, 3, 9):
-    ops.set_conv_chunk_taps(taps)
+for taps in (1, -6, -9, 3, 9):
+    if taps < 0:
+        ops.set_conv_chunk_kblocks(-taps)          # K-blocks of 64 channels per chunk (1.5 / 2.25 taps)
+    else:
+        ops.set_conv_chunk_kblocks(0)
+        ops.set_conv_chunk_taps(taps)
     res, raw, cand, det = pred.infer_from_features(feats, (H, W), (H, W), image0=0, seed=7, return_raw=True)
     torch.cuda.synchronize()
     dl = max(float((raw["logits"][0, s].cpu() - torch.cat([o[0] for o in outs[s]["box_cls"]], 0)).abs().max()) for s in range(N))
@@ -44,8 +48,9 @@ for taps in (1, 3, 9):
     bx = cand["boxes"][0, :M].cpu().numpy()[ig]; bxr = ref_cand.boxes.numpy()[ir]
     cv = cand["cov"][0, :M].cpu().numpy()[ig].astype(np.float64); cvr = ref_cand.cov.numpy()[ir].astype(np.float64)
     scale = np.abs(cvr).reshape(len(ir), -1).max(1).reshape(-1, 1, 1)
-    print("chunk = %d tap(s): max|dlogit| %.2e  max|ddelta| %.2e | candidates %d/%d common | score rel %.2e | box abs %.2e px | "
+    print("chunk = %s: max|dlogit| %.2e  max|ddelta| %.2e | candidates %d/%d common | score rel %.2e | box abs %.2e px | "
           "cov rel(matrix max) %.2e | detections %d vs %d"
-          % (taps, dl, dd, len(common), ref_cand.boxes.shape[0], float(np.abs(sc / scr - 1).max()), float(np.abs(bx - bxr).max()),
+          % (("%d tap(s)" % taps) if taps > 0 else ("%d K-blocks" % -taps), dl, dd, len(common), ref_cand.boxes.shape[0], float(np.abs(sc / scr - 1).max()), float(np.abs(bx - bxr).max()),
              float((np.abs(cv - cvr) / scale).max()), len(res[0]), ref_final.boxes.shape[0]))
+ops.set_conv_chunk_kblocks(0)
 ops.set_conv_chunk_taps(1)
