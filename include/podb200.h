@@ -124,8 +124,8 @@ int pod_conv3x3_tc_set_kblock(int bk);
  * the epilogue warps: 1 (default, most accurate), 3 or 9 (single chain; tcgen05 accumulates with
  * truncation, which drifts ~2e-5 relative over the 2304-long reduction). */
 int pod_conv3x3_tc_set_chunk_taps(int taps);
-/* Finer control: K-blocks per accumulation chunk (0 = use the taps setting); ignored for a convolution whose
- * K-block count it does not divide. */
+/* Finer control: K-blocks per accumulation chunk (default 6 = 384 channels = 1.5 taps; 0 = use the taps
+ * setting); ignored for a convolution whose K-block count it does not divide. */
 int pod_conv3x3_tc_set_chunk_kblocks(int kb);
 /* 256-output-channel convolutions on CTA pairs (tcgen05 cta_group::2, default on) or on single CTAs. */
 int pod_conv3x3_tc_set_pair(int on);

@@ -790,7 +790,8 @@ static int dispatch_bn(const Params& P, cudaStream_t st) {
 
 static int g_tc_bk = 64;      // K-block (channels per pipeline stage): 64 -> SWIZZLE_128B (default), 32 -> SWIZZLE_64B
 static int g_tc_taps = 1;     // taps per accumulation chunk (1, 3 or 9)
-static int g_tc_chunk_kb = 0; // if > 0: K-blocks per accumulation chunk (must divide 9*Cin/K-block); overrides taps
+static int g_tc_chunk_kb = 6; // if > 0: K-blocks per accumulation chunk (must divide 9*Cin/K-block); overrides taps.
+                              // default 6 x 64 channels = 1.5 taps: 6 TMEM drains per tile (measured trade-off in DESIGN.md)
 
 extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_chunk_kblocks(int kb) {
   POD_REQUIRE(kb >= 0, "pod_conv3x3_tc_set_chunk_kblocks: must be >= 0");

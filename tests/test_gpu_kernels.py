@@ -148,11 +148,13 @@ def test_tc_conv_chunked_accumulation_is_more_accurate():
     ref = G.conv_ref64(x, w, b, False)
     err = {}
     try:
+        ops.set_conv_chunk_kblocks(0)
         for taps in (9, 1):
             ops.set_conv_chunk_taps(taps)
             err[taps] = G.rel_err(G.tc_conv_raw(x, w, b, False), ref)
     finally:
         ops.set_conv_chunk_taps(1)
+        ops.set_conv_chunk_kblocks(6)
     print("conv rel err vs fp64: single chain %.3e, per-tap chunks %.3e" % (err[9], err[1]))
     assert err[1] < 3e-6
     assert err[1] < err[9]

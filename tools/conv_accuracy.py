@@ -29,10 +29,12 @@ def stats(got):
 
 print("shape", (NB, C, H, W), "-> 256 channels, K = 2304")
 print("fp32 CPU conv (reference arithmetic):", stats(cpu))
+ops.set_conv_chunk_kblocks(0)
 for taps in (9, 3, 1):
     ops.set_conv_chunk_taps(taps)
     for kb in (32, 64):
         ops.set_conv_kblock(kb)
         print("tcgen05 fp16x3, chunk = %d tap(s), kblock %d:" % (taps, kb), stats(G.tc_conv_raw(x, w, b, False)))
 ops.set_conv_chunk_taps(1)
+ops.set_conv_chunk_kblocks(6)
 ops.set_conv_kblock(64)

@@ -52,5 +52,5 @@ for taps in (1, -6, -9, 3, 9):
           "cov rel(matrix max) %.2e | detections %d vs %d"
           % (("%d tap(s)" % taps) if taps > 0 else ("%d K-blocks" % -taps), dl, dd, len(common), ref_cand.boxes.shape[0], float(np.abs(sc / scr - 1).max()), float(np.abs(bx - bxr).max()),
              float((np.abs(cv - cvr) / scale).max()), len(res[0]), ref_final.boxes.shape[0]))
-ops.set_conv_chunk_kblocks(0)
 ops.set_conv_chunk_taps(1)
+ops.set_conv_chunk_kblocks(6)
