@@ -308,8 +308,13 @@ def main():
         torch.cuda.synchronize()
         tot_ms, tot_flop, n = 0.0, 0.0, 0
         all_ms = 0.0
+        hbm = {}
         for (s, e, flop, tag) in prof:
             d = s.elapsed_time(e)
+            if tag in ("mask_expand", "sample_mean"):
+                h = hbm.setdefault(tag, [0.0, 0.0, 0])
+                h[0] += d; h[1] += flop; h[2] += 1
+                continue
             all_ms += d
             if tag == "tower256":
                 tot_ms += d
@@ -336,12 +341,21 @@ def main():
                     "note": "achieved counts ALGORITHMIC fp32 FLOPs (2*9*256*256 per location); each is issued as 3 fp16 "
                             "tensor-core MMAs (hi*hi, hi*lo, lo*hi), so frac <= 1/3 by construction and mma_frac is the "
                             "tensor-pipe utilisation"}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_kernels = {}
+    if prof:
+        names = {"mask_expand": "k_mask_expand (first-layer MC replication: 1 fp32 read, N x passes split-pair writes)",
+                 "sample_mean": "k_sample_mean_q1 (per-anchor statistics: Q1 mean over the N samples)"}
+        for tag, (t_ms, nbytes, cnt) in hbm.items():
+            gbs = nbytes / (t_ms / 1000.0) / 1e9
+            hbm_kernels[tag] = {"kernel": names[tag], "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": gbs / hbm_peak, "launches": cnt, "share_of_step": t_ms / ms}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (fp16x3 split operands on tcgen05, fp32 accumulate)", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
-            "gpu_launches": launches, "roofline": roof}
+            "gpu_launches": launches, "roofline": roof, "hbm_kernels": hbm_kernels}
     if args.workload != "mc_pre":
         line["metric"] = "images/sec, side workload (not the BASELINE headline)"
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "mc_pre":

@@ -99,43 +99,48 @@ extern "C" __attribute__((visibility("default"))) int pod_pack_conv_weight_f32(c
 // ---------------------------------------------------------------------------------------------
 // MC-dropout replication of the first tower layer: one read, samples*passes masked split copies
 // ---------------------------------------------------------------------------------------------
-__global__ void k_mask_expand(const float* __restrict__ x, int64_t quads_per_map, int NB_in, pod_dropout d, float scale,
-                              uint32_t thr, float dscale, PhiloxKey key, __half* __restrict__ hi,
-                              __half* __restrict__ lo) {
+// one thread = 8 consecutive channels (two Philox quads): 32-byte loads, 16-byte stores per copy
+__global__ void __launch_bounds__(256)
+k_mask_expand(const float* __restrict__ x, int64_t oct_per_map, int NB_in, pod_dropout d, float scale,
+              uint32_t thr, float dscale, PhiloxKey key, __half* __restrict__ hi, __half* __restrict__ lo) {
   const int reps = d.samples * d.passes;
-  const int64_t total = quads_per_map * NB_in;
+  const int64_t total = oct_per_map * NB_in;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int nb = (int)(t / quads_per_map);
-    const int64_t q = t % quads_per_map;
-    const float4 v = reinterpret_cast<const float4*>(x)[t];
+    const int nb = (int)(t / oct_per_map);
+    const int64_t o8 = t % oct_per_map;
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(x) + 2 * t);
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(x) + 2 * t + 1);
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    const uint32_t image = (uint32_t)(d.image0 + nb);
     for (int r = 0; r < reps; ++r) {
       const int sample = r / d.passes, pass = d.pass0 + r % d.passes;
-      const uint4 w = philox4x32_10((uint32_t)q, pod_dropout_c1(d.level, d.layer, d.tower, pass), (uint32_t)sample,
-                                    (uint32_t)(d.image0 + nb), key);
-      float o[4];
-      o[0] = w.x >= thr ? v.x * dscale : 0.f;
-      o[1] = w.y >= thr ? v.y * dscale : 0.f;
-      o[2] = w.z >= thr ? v.z * dscale : 0.f;
-      o[3] = w.w >= thr ? v.w * dscale : 0.f;
-      __half h[4], l[4];
+      const uint32_t c1 = pod_dropout_c1(d.level, d.layer, d.tower, pass);
+      const uint4 wa = philox4x32_10((uint32_t)(2 * o8), c1, (uint32_t)sample, image, key);
+      const uint4 wb = philox4x32_10((uint32_t)(2 * o8 + 1), c1, (uint32_t)sample, image, key);
+      const uint32_t w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+      uint32_t ph[4], pl[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) pod_split_h(o[i] * scale, h[i], l[i]);
-      const int64_t oq = ((int64_t)nb * reps + r) * quads_per_map + q;
-      reinterpret_cast<uint2*>(hi)[oq] = make_uint2(
-          (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
-          (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
-      reinterpret_cast<uint2*>(lo)[oq] = make_uint2(
-          (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
-          (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+      for (int i = 0; i < 4; ++i) {
+        const float a = w[2 * i] >= thr ? v[2 * i] * dscale : 0.f;
+        const float b = w[2 * i + 1] >= thr ? v[2 * i + 1] * dscale : 0.f;
+        __half h0, l0, h1, l1;
+        pod_split_h(a * scale, h0, l0);
+        pod_split_h(b * scale, h1, l1);
+        ph[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        pl[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      }
+      const int64_t oq = ((int64_t)nb * reps + r) * oct_per_map + o8;
+      __stcs(reinterpret_cast<uint4*>(hi) + oq, make_uint4(ph[0], ph[1], ph[2], ph[3]));   // streaming: written once,
+      __stcs(reinterpret_cast<uint4*>(lo) + oq, make_uint4(pl[0], pl[1], pl[2], pl[3]));   // read by the next conv via TMA
     }
   }
 }
 
 extern "C" __attribute__((visibility("default"))) int pod_mask_expand_split(const float* x, int NB_in, int HW, int C, const pod_dropout* d, float scale,
                                      void* dst_hi, void* dst_lo, void* stream) {
-  POD_REQUIRE(x && d && dst_hi && dst_lo && NB_in > 0 && HW > 0 && C > 0 && C % 4 == 0, "pod_mask_expand_split: bad args");
+  POD_REQUIRE(x && d && dst_hi && dst_lo && NB_in > 0 && HW > 0 && C > 0 && C % 8 == 0, "pod_mask_expand_split: bad args (C%%8)");
   POD_REQUIRE(d->samples > 0 && d->passes > 0 && d->p > 0.0 && d->p < 1.0, "pod_mask_expand_split: bad dropout spec");
-  const int64_t qpm = (int64_t)HW * C / 4;
+  const int64_t qpm = (int64_t)HW * C / 8;
   const int64_t total = qpm * NB_in;
   const int grid = (int)((total + 255) / 256 < (int64_t)pod_num_sms() * 16 ? (total + 255) / 256 : (int64_t)pod_num_sms() * 16);
   k_mask_expand<<<grid, 256, 0, (cudaStream_t)stream>>>(x, qpm, NB_in, *d, scale, pod_dropout_threshold(d->p),

@@ -127,8 +127,14 @@ def mask_expand_split(x, drop, scale, out_hi=None, out_lo=None):
         out_hi = torch.empty((NB * reps, HW, Cn), dtype=torch.float16, device=x.device)
         out_lo = torch.empty_like(out_hi)
     assert out_hi.numel() >= NB * reps * HW * Cn and out_lo.numel() >= NB * reps * HW * Cn
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib.pod_mask_expand_split(ptr(x), NB, HW, Cn, C.byref(drop), scale, ptr(out_hi), ptr(out_lo), stream_ptr()),
           "pod_mask_expand_split")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append((e0, e1, 4.0 * NB * HW * Cn * (1 + reps), "mask_expand"))     # algorithmic bytes: 1 read + reps writes
     _count()
     return out_hi, out_lo
 
@@ -212,7 +218,13 @@ def sample_mean_q1(x):
     B, S = x.shape[0], x.shape[1]
     n = x[0, 0].numel()
     out = torch.empty((B,) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib.pod_sample_mean_q1(ptr(x), B, S, n, ptr(out), stream_ptr()), "pod_sample_mean_q1")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append((e0, e1, 4.0 * B * n * (max(S - 1, 1) + 1), "sample_mean"))   # reads S-1 samples (Q1), writes 1
     _count()
     return out
 
