@@ -36,7 +36,9 @@ class ConvArgs(C.Structure):
                 ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("w_scale", C.c_float), ("bias", C.c_void_p),
                 ("Cout", C.c_int), ("Cout_pad", C.c_int), ("mode", C.c_int), ("relu", C.c_int),
                 ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_scale", C.c_float), ("out_f32", C.c_void_p),
-                ("out_map_stride", C.c_int64), ("out_pixel_stride", C.c_int64), ("drop", Dropout)]
+                ("out_map_stride", C.c_int64), ("out_pixel_stride", C.c_int64), ("drop", Dropout),
+                ("out2_f32", C.c_void_p), ("split_col", C.c_int), ("out2_map_stride", C.c_int64),
+                ("out2_pixel_stride", C.c_int64)]
 
 
 class DecodeArgs(C.Structure):

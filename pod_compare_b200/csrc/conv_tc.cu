@@ -49,6 +49,9 @@ struct Params {
   __half* out_lo;
   float* out_f32;
   long long out_map_stride, out_pixel_stride;
+  float* out2_f32;      // optional second RAW destination for channels >= split_c
+  int split_c;
+  long long out2_map_stride, out2_pixel_stride;
   pod_dropout drop;
   uint32_t drop_thr;
   float drop_scale;
@@ -243,7 +246,14 @@ __device__ __forceinline__ void tile_epilogue(const Params& P, const float (&sum
         dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
       } else {
         float* o = P.out_f32 + (long long)n * P.out_map_stride + (long long)pixel * P.out_pixel_stride + ch;
-        if (ch + 16 <= P.Cout && ((P.out_map_stride | P.out_pixel_stride) & 3) == 0) {
+        if (P.out2_f32 != nullptr) {
+          float* o2 = P.out2_f32 + (long long)n * P.out2_map_stride + (long long)pixel * P.out2_pixel_stride + (ch - P.split_c);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (ch + i < P.split_c) o[i] = v[i];
+            else if (ch + i < P.Cout) o2[i] = v[i];
+          }
+        } else if (ch + 16 <= P.Cout && ((P.out_map_stride | P.out_pixel_stride) & 3) == 0) {
           float4* o4 = reinterpret_cast<float4*>(o);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) o4[q4] = make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
@@ -853,6 +863,10 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   P.bias = a->bias;
   P.out_hi = (__half*)a->out_hi; P.out_lo = (__half*)a->out_lo; P.out_f32 = a->out_f32;
   P.out_map_stride = a->out_map_stride; P.out_pixel_stride = a->out_pixel_stride;
+  if (a->mode == POD_OUT_RAW && a->out2_f32 != nullptr) {
+    P.out2_f32 = a->out2_f32; P.split_c = a->split_col;
+    P.out2_map_stride = a->out2_map_stride; P.out2_pixel_stride = a->out2_pixel_stride;
+  }
   P.drop = a->drop;
   if (P.drop.samples <= 0) P.drop.samples = 1;
   if (P.drop.passes <= 0) P.drop.passes = 1;

@@ -89,6 +89,15 @@ class HeadWeights:
         self.bbox_pred = pack_conv_blocks(sd["head.bbox_pred.weight"], sd["head.bbox_pred.bias"], device)
         self.cls_var = pack_conv_blocks(sd["head.cls_var.weight"], sd["head.cls_var.bias"], device) if cls_var else None
         self.bbox_cov = pack_conv_blocks(sd["head.bbox_cov.weight"], sd["head.bbox_cov.bias"], device) if bbox_cov else None
+        # eval mode: both heads of a tower read the same activations, so mean|variance weights are also packed
+        # as ONE convolution (rows [mean; var]) whose epilogue routes the two column ranges to their buffers
+        self.cls_fused = self.box_fused = None
+        if cls_var and not use_dropout:
+            self.cls_fused = pack_conv_blocks(torch.cat([sd["head.cls_score.weight"], sd["head.cls_var.weight"]], 0),
+                                              torch.cat([sd["head.cls_score.bias"], sd["head.cls_var.bias"]], 0), device)
+        if bbox_cov and not use_dropout:
+            self.box_fused = pack_conv_blocks(torch.cat([sd["head.bbox_pred.weight"], sd["head.bbox_cov.weight"]], 0),
+                                              torch.cat([sd["head.bbox_pred.bias"], sd["head.bbox_cov.bias"]], 0), device)
 
 
 @dataclass
@@ -232,6 +241,19 @@ class HeadEngine:
                     mean_pc, var_pc = (w.cls_score, w.cls_var) if tower == TOWER_CLS else (w.bbox_pred, w.bbox_cov)
                     mean_out = raw["logits"] if tower == TOWER_CLS else raw["deltas"]
                     D = mean_pc[0].total_cout // A
+                    fused = w.cls_fused if tower == TOWER_CLS else w.box_fused
+                    if fused is not None:
+                        var_out = raw["logvar"] if tower == TOWER_CLS else raw["regvar"]
+                        Dv = var_pc[0].total_cout // A
+                        split = mean_pc[0].total_cout
+                        for pcv in fused:
+                            ops.conv3x3_tc(src[0], src[1], ACT_SCALE, B, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias,
+                                           pcv.cout, pcv.cout_pad, POD_OUT_RAW, False,
+                                           out_f32=mean_out, out_offset=(e * R + level_off[lvl]) * D + pcv.col0,
+                                           out_map_stride=E * R * D, out_pixel_stride=A * D,
+                                           out2_f32=var_out, out2_offset=(e * R + level_off[lvl]) * Dv,
+                                           split_col=split - pcv.col0, out2_map_stride=E * R * Dv, out2_pixel_stride=A * Dv)
+                        continue
                     self._conv_out(src, B, H, W, mean_pc, mean_out, (e * R + level_off[lvl]) * D, E * R * D)
                     if var_pc is not None:
                         var_out = raw["logvar"] if tower == TOWER_CLS else raw["regvar"]

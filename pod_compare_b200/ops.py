@@ -141,7 +141,8 @@ def mask_expand_split(x, drop, scale, out_hi=None, out_lo=None):
 
 def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias, Cout, Cout_pad, mode, relu,
                out_hi=None, out_lo=None, out_scale=1.0, out_f32=None, out_map_stride=0, out_pixel_stride=0,
-               drop=None, in_map_stride=None, in_offset=0, out_offset=0):
+               drop=None, in_map_stride=None, in_offset=0, out_offset=0, out2_f32=None, out2_offset=0, split_col=0,
+               out2_map_stride=0, out2_pixel_stride=0):
     """Raw-pointer launch of the tcgen05 convolution. `in_offset`/`out_offset` are ELEMENT offsets
     into in_hi/in_lo and out_f32."""
     lib = _cabi.require_device()
@@ -161,6 +162,9 @@ def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias,
     a.out_f32 = (out_f32.data_ptr() + out_offset * 4) if out_f32 is not None else None
     a.out_map_stride, a.out_pixel_stride = out_map_stride, out_pixel_stride
     a.drop = drop if drop is not None else make_dropout()
+    if out2_f32 is not None:
+        a.out2_f32 = out2_f32.data_ptr() + out2_offset * 4
+        a.split_col, a.out2_map_stride, a.out2_pixel_stride = split_col, out2_map_stride, out2_pixel_stride
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

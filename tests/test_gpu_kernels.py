@@ -327,3 +327,24 @@ def test_topk_random_levels_with_ties(seed):
                 order = order[sc[order] > thr]
                 assert int(cand_cnt[b, l]) == order.numel(), (seed, topk, b, l)
                 assert torch.equal(cand_idx[b, seg[l]:seg[l] + order.numel()].long(), order + off[l])
+
+
+def test_tc_conv_dual_destination_raw():
+    """One launch, two heads: channels [0,63) -> first buffer, [63,126) -> second (eval-mode cls_score|cls_var)."""
+    g = torch.Generator().manual_seed(21)
+    NB, H, W = 2, 9, 13
+    x = torch.randn((NB, 256, H, W), generator=g)
+    w = torch.randn((126, 256, 3, 3), generator=g) * (2.0 / 2304) ** 0.5
+    b = torch.randn((126,), generator=g) * 0.1
+    hi, lo = ops.nchw_to_nhwc_split(x.cuda(), 16.0)
+    pcv = engine.pack_conv(w, b, "cuda")
+    o1 = torch.full((NB, H * W, 63), float("nan"), device="cuda")
+    o2 = torch.full((NB, H * W, 63), float("nan"), device="cuda")
+    ops.conv3x3_tc(hi, lo, 16.0, NB, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, 126, pcv.cout_pad, G.POD_OUT_RAW,
+                   False, out_f32=o1, out_map_stride=H * W * 63, out_pixel_stride=63, out2_f32=o2, split_col=63,
+                   out2_map_stride=H * W * 63, out2_pixel_stride=63)
+    torch.cuda.synchronize()
+    ref = G.conv_ref64(x, w, b, False)
+    got1 = o1.view(NB, H, W, 63).permute(0, 3, 1, 2).cpu()
+    got2 = o2.view(NB, H, W, 63).permute(0, 3, 1, 2).cpu()
+    assert G.rel_err(got1, ref[:, :63]) < 1e-5 and G.rel_err(got2, ref[:, 63:]) < 1e-5
