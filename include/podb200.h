@@ -116,9 +116,10 @@ typedef struct pod_conv_args {
   int64_t out_pixel_stride;
   pod_dropout drop;
   /* POD_OUT_RAW only, optional second destination: output channels c >= split_col go to
-     * out2_f32[n*out2_map_stride + pixel*out2_pixel_stride + (c - split_col)]; out2_f32 == NULL: single
-   * destination.  split_col may be <= 0 (every channel of this launch belongs to the second destination).  Lets one launch evaluate two heads that read the same tower output (eval mode:
-   * cls_score|cls_var, bbox_pred|bbox_cov -- probabilistic_retinanet.py:518-523 with identical tower passes). */
+   * out2_f32[n*out2_map_stride + pixel*out2_pixel_stride + (c - split_col)]; out2_f32 == NULL means a single
+   * destination.  split_col may be <= 0 (every channel of this launch belongs to the second destination).
+   * Lets one launch evaluate two heads that read the same tower output (eval mode: cls_score|cls_var and
+   * bbox_pred|bbox_cov, probabilistic_retinanet.py:518-523 with identical tower passes). */
   float* out2_f32;
   int split_col;
   int64_t out2_map_stride;

@@ -883,7 +883,14 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
       P.key = pod_key(a->drop.seed, POD_STREAM_DROPOUT);
     }
   } else if (a->mode == POD_OUT_RAW) {
-    POD_REQUIRE(a->out_f32 && a->out_pixel_stride >= a->Cout, "pod_conv3x3_tc: raw mode needs out_f32 / pixel stride");
+    POD_REQUIRE(a->out_f32 && a->out_pixel_stride > 0, "pod_conv3x3_tc: raw mode needs out_f32 / pixel stride");
+    if (a->out2_f32 == nullptr) {
+      POD_REQUIRE(a->out_pixel_stride >= a->Cout, "pod_conv3x3_tc: raw mode pixel stride smaller than Cout");
+    } else {
+      const int n1 = a->split_col < 0 ? 0 : (a->split_col < a->Cout ? a->split_col : a->Cout);
+      POD_REQUIRE(a->out_pixel_stride >= n1 && a->out2_pixel_stride >= a->Cout - n1 && a->out2_pixel_stride > 0,
+                  "pod_conv3x3_tc: dual-destination pixel strides too small");
+    }
   } else {
     POD_REQUIRE(false, "pod_conv3x3_tc: unknown mode %d", a->mode);
   }
