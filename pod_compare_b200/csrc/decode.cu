@@ -1,6 +1,7 @@
 // Candidate decode: anchor deltas -> boxes with aleatoric (1000-draw Monte-Carlo) and epistemic
 // (over MC-dropout samples / ensemble members) covariance.  One warp per candidate; draws are
-// generated in-register from the Philox stream, nothing of size M x 1000 is ever materialised.
+// generated in-register from the Philox stream (one pass, shifted moments), nothing of size M x 1000 is
+// ever materialised.
 // Replaces /root/reference/src/probabilistic_inference/probabilistic_inference.py:310-388,
 // inference_utils.py:337-371 (compute_mean_covariance_torch), :510-547 (apply_samples_deltas) and
 // probabilistic_modeling/modeling_utils.py:4-22 (covariance_output_to_cholesky).
@@ -49,32 +50,42 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // mean and unbiased covariance of `count` boxes produced by gen(j, box) for j = lane, lane+32, ...
-// (two passes; the generator is re-evaluated, the shift `ref` keeps the fp32 sums small)
+// One pass over the draws with moments taken about `ref` (the analytic decode of the mean delta, within
+// a fraction of a standard deviation of the sample mean), so the fp32 sums stay small and the final
+// correction  cov = (S2 - S1 S1^T / n) / (n - 1)  does not cancel.
 template <class Gen>
 __device__ __forceinline__ void mean_cov(int count, int lane, const float ref[4], Gen gen, float mean[4], float cov[10]) {
   float s[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int j = lane; j < count; j += 32) {
-    float x[4];
-    gen(j, x);
-#pragma unroll
-    for (int d = 0; d < 4; ++d) s[d] += x[d] - ref[d];
-  }
-#pragma unroll
-  for (int d = 0; d < 4; ++d) mean[d] = ref[d] + warp_sum(s[d]) / (float)count;
   float c[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int j = lane; j < count; j += 32) {
     float x[4], r[4];
     gen(j, x);
 #pragma unroll
-    for (int d = 0; d < 4; ++d) r[d] = x[d] - mean[d];
+    for (int d = 0; d < 4; ++d) {
+      r[d] = x[d] - ref[d];
+      s[d] += r[d];
+    }
     int q = 0;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int bb = a; bb < 4; ++bb) c[q++] += r[a] * r[bb];
   }
+  const float inv_n = 1.0f / (float)count;
 #pragma unroll
-  for (int q = 0; q < 10; ++q) cov[q] = warp_sum(c[q]) / (float)(count - 1);
+  for (int d = 0; d < 4; ++d) {
+    s[d] = warp_sum(s[d]);
+    mean[d] = ref[d] + s[d] * inv_n;
+  }
+  int q = 0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int bb = a; bb < 4; ++bb) {
+      const float s2 = warp_sum(c[q]);
+      cov[q] = (s2 - s[a] * s[bb] * inv_n) / (float)(count - 1);
+      ++q;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_decode(pod_decode_args a, SegTable st, PhiloxKey key, float clampv) {
