@@ -139,8 +139,17 @@ class HeadEngine:
         return t
 
     # ------------------------------------------------------------------ head
-    def _conv_hidden(self, src, NB, H, W, pcv, dst, drop):
-        ops.conv3x3_tc(src[0], src[1], ACT_SCALE, NB, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, pcv.cout,
+    @staticmethod
+    def feature_scale(feats):
+        """fp16 split scale of the input maps: ACT_SCALE unless a feature exceeds its range (|x|*scale must stay
+        below fp16's 65504), in which case the largest smaller power of two.  One device reduction + sync."""
+        amax = float(torch.stack([f.abs().amax() for f in feats]).max())
+        if not math.isfinite(amax):
+            raise PodError("non-finite values in the input feature maps")
+        return min(ACT_SCALE, ops.pow2_scale(amax, 32768.0)) if amax > 0 else ACT_SCALE
+
+    def _conv_hidden(self, src, NB, H, W, pcv, dst, drop, in_scale=ACT_SCALE):
+        ops.conv3x3_tc(src[0], src[1], in_scale, NB, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, pcv.cout,
                        pcv.cout_pad, POD_OUT_HIDDEN, True, out_hi=dst[0], out_lo=dst[1], out_scale=ACT_SCALE, drop=drop)
 
     def _conv_out(self, src, NB, H, W, blocks, out, out_offset, out_map_stride, in_map_stride=None, in_offset=0):
@@ -172,17 +181,18 @@ class HeadEngine:
         act = [(self._get("a%d_hi" % i, nmaps * max_hw * 256, torch.float16),
                 self._get("a%d_lo" % i, nmaps * max_hw * 256, torch.float16)) for i in range(2)]
         c1 = self._get("c1", B * max_hw * 256, torch.float32)
+        fscale = self.feature_scale(feats)
         for lvl, f in enumerate(feats):
             H, W = level_hw[lvl]
             HW = H * W
-            fhi, flo = ops.nchw_to_nhwc_split(f.contiguous(), ACT_SCALE)
+            fhi, flo = ops.nchw_to_nhwc_split(f.contiguous(), fscale)
             for tower in (TOWER_CLS, TOWER_BOX):
                 tw = w.towers[tower]
                 has_var = pc.cls_var if tower == TOWER_CLS else pc.bbox_cov
                 t_passes = 2 if has_var else 1
                 # layer 0: conv + ReLU once per image, then N x passes masked copies (Q2 hoist)
                 p0 = tw[0]
-                ops.conv3x3_tc(fhi, flo, ACT_SCALE, B, H, W, 256, p0.w_hi, p0.w_lo, p0.w_scale, p0.bias, 256, 256,
+                ops.conv3x3_tc(fhi, flo, fscale, B, H, W, 256, p0.w_hi, p0.w_lo, p0.w_scale, p0.bias, 256, 256,
                                POD_OUT_RAW, True, out_f32=c1, out_map_stride=HW * 256, out_pixel_stride=256)
                 d0 = ops.make_dropout(pc.dropout_rate, seed, image0, n_mc, t_passes, 0, tower, 0, lvl)
                 ops.mask_expand_split(c1[: B * HW * 256].view(B, HW, 256), d0, ACT_SCALE, act[0][0], act[0][1])
@@ -226,16 +236,17 @@ class HeadEngine:
         max_hw = max(h * wd for h, wd in level_hw)
         act = [(self._get("a%d_hi" % i, B * max_hw * 256, torch.float16),
                 self._get("a%d_lo" % i, B * max_hw * 256, torch.float16)) for i in range(2)]
+        fscale = self.feature_scale(feats)
         for lvl, f in enumerate(feats):
             H, W = level_hw[lvl]
-            fhi, flo = ops.nchw_to_nhwc_split(f.contiguous(), ACT_SCALE)
+            fhi, flo = ops.nchw_to_nhwc_split(f.contiguous(), fscale)
             for e, mi in enumerate(members):
                 w = self.ws[mi]
                 for tower in (TOWER_CLS, TOWER_BOX):
                     tw = w.towers[tower]
                     src, cur = (fhi, flo), 0
                     for layer in range(len(tw)):
-                        self._conv_hidden(src, B, H, W, tw[layer], act[cur], None)
+                        self._conv_hidden(src, B, H, W, tw[layer], act[cur], None, in_scale=fscale if layer == 0 else ACT_SCALE)
                         src = act[cur]
                         cur ^= 1
                     mean_pc, var_pc = (w.cls_score, w.cls_var) if tower == TOWER_CLS else (w.bbox_pred, w.bbox_cov)

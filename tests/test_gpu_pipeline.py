@@ -469,3 +469,21 @@ def test_predictor_from_raw_images_with_backbone():
     assert [tuple(f.shape[-2:]) for f in feats] == [(16, 32), (8, 16), (4, 8), (2, 4), (1, 2)]
     ref = pred.infer_from_features(feats, (96, 160), (96, 160), image0=0)[0]
     assert len(inst) == len(ref) and torch.equal(inst.pred_boxes.tensor, ref.pred_boxes.tensor)
+
+
+def test_large_feature_magnitudes_are_rescaled():
+    """Feature maps beyond the default fp16 split range (|x|*16 > 65504) get a smaller power-of-two scale
+    instead of overflowing: results equal the oracle on the same (large) inputs."""
+    name = "regclsvar_std"
+    opts, mode, n_mc, seeds, hw, out_hw, seed, img = C.CASES[name]
+    cfg, pp, sds, feats = _oracle_case(name)
+    feats = [f * 3000.0 for f in feats]
+    sd = {k: (v / 3000.0 if k.endswith(".0.weight") and "subnet" in k else v) for k, v in sds[0].items()}
+    pred = build_predictor(cfg)
+    pred.load_weight_sets(sd)
+    res, _, cand, det = pred.infer_from_features(feats, hw, out_hw, image0=img, seed=seed, return_candidates=True)
+    torch.set_num_threads(8)
+    ref_final, ref_cand, ref_det = O.predict(feats, [O.unpack_head(sd, pp)], pp, mode, hw, out_hw=out_hw, n_mc=n_mc, seed=seed,
+                                             image=img, return_candidates=True, keep_diag=True)
+    assert torch.isfinite(res[0].scores).all()
+    _compare_path(res[0], cand, det, ref_final, ref_cand, ref_det, pp, False)
