@@ -194,6 +194,7 @@ def main():
                     help="mc_pre = the headline metric (BASELINE configs[2]); the others are side measurements")
     ap.add_argument("--kblock", type=int, default=0)
     ap.add_argument("--pair", type=int, default=-1, help="1/0: force CTA-pair (cta_group::2) / single-CTA tower convs")
+    ap.add_argument("--halo", type=int, default=-1, help="1/0: row-halo activation staging on / one TMA box per tap")
     ap.add_argument("--chunk-taps", type=int, default=0, help="taps per accumulation chunk (1, 3, 9)")
     ap.add_argument("--chunk-kblocks", type=int, default=0, help="K-blocks per accumulation chunk (overrides --chunk-taps)")
     args = ap.parse_args()
@@ -215,6 +216,8 @@ def main():
         ops.set_conv_kblock(args.kblock)
     if args.pair >= 0:
         ops.set_conv_pair(args.pair)
+    if args.halo >= 0:
+        ops.set_conv_halo(args.halo)
     if args.chunk_taps:
         ops.set_conv_chunk_taps(args.chunk_taps)
     if args.chunk_kblocks:
@@ -309,8 +312,10 @@ def main():
         tot_ms, tot_flop, n = 0.0, 0.0, 0
         all_ms = 0.0
         hbm = {}
+        by_tag = {}
         for (s, e, flop, tag) in prof:
             d = s.elapsed_time(e)
+            by_tag[tag] = by_tag.get(tag, 0.0) + d / args.steps
             if tag in ("mask_expand", "sample_mean"):
                 h = hbm.setdefault(tag, [0.0, 0.0, 0])
                 h[0] += d; h[1] += flop; h[2] += 1
@@ -338,6 +343,7 @@ def main():
                     "algorithmic_flop_per_launch": tot_flop / n,
                     "mma_tflops": 3.0 * ach, "mma_frac": 3.0 * ach / peak,
                     "conv_share_of_step": all_ms / ms,
+                    "ms_per_step_by_kernel": {k: round(v, 3) for k, v in sorted(by_tag.items())},
                     "note": "achieved counts ALGORITHMIC fp32 FLOPs (2*9*256*256 per location); each is issued as 3 fp16 "
                             "tensor-core MMAs (hi*hi, hi*lo, lo*hi), so frac <= 1/3 by construction and mma_frac is the "
                             "tensor-pipe utilisation"}

@@ -8,7 +8,7 @@
 // * B operand: packed weight rows [Cout_pad][9*Cin] fetched by TMA (2-D map).
 // * fp32 fidelity on fp16 tensor cores: both operands arrive as (hi, lo) fp16 pairs and every
 //   K-step issues three tcgen05.mma (hi*hi', hi*lo', lo*hi') into one fp32 TMEM accumulator.
-// * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
+// * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
 //   warps 4-7 = epilogue (tcgen05.ld -> bias/ReLU/Philox dropout -> fp16 split or fp32 store).
 //   Two TMEM accumulators (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 // * persistent: grid = min(#tiles, #SMs), static round-robin over (map, tile_y, tile_x).
@@ -120,18 +120,34 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
+// One lane of a CONVERGED warp (elect.sync).  The MMA-issuing warp runs its whole loop with warp-uniform control
+// flow and predicates every tcgen05.mma / tcgen05.commit on this flag: ptxas then emits straight-line UTCHMMA
+// from uniform registers.  Issued from divergent code (`if (lane == 0)`) each tcgen05 instruction is instead
+// wrapped in an ELECT / BRA.U.ANY serialisation loop (~100 cycles per MMA, measured: the narrow output
+// convolutions were bound by that issue rate, not by the tensor pipe or L2).
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
 // D[tmem] (+)= A[smem] * B[smem], fp16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                         uint32_t leader) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(leader) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -155,6 +171,11 @@ __device__ __forceinline__ bool warp_mbar_wait(uint64_t* bar, uint32_t parity, i
   int ok = 1;
   if (lane == 0) ok = mbar_wait(bar, parity, code) ? 1 : 0;
   return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
+// every lane of a converged warp waits (each observes the phase flip); warp-uniform result
+__device__ __forceinline__ bool mbar_wait_all(uint64_t* bar, uint32_t parity, int code) {
+  const bool ok = mbar_wait(bar, parity, code);
+  return __all_sync(0xffffffffu, ok) != 0;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -182,6 +203,48 @@ struct Cfg {
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 512 == 0, "operand alignment");
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major both, N>>3, M>>4
   static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Row-halo staging (HALO kernels, K-block 64 only).  The nine shifted 8x16 boxes of a pixel tile overlap:
+// for a fixed column shift dx the three row shifts dy read rows y0-1+dy .. y0+6+dy of the same 16 columns.
+// One TMA box of 10 rows x 16 columns x 64 channels therefore serves three taps, and because a row of the
+// staged box is 16 pixels x 128 B = 2048 B (two whole SWIZZLE_128B atoms) the tap dy is simply the shared-
+// memory descriptor advanced by dy*2048 B -- still 1024-B aligned, so the swizzle pattern is untouched.
+// Activation bytes into the SM drop from 9 x 128 to 3 x 160 pixel rows per K-block (2.4x less); the
+// L2->SM path (~43 B/clk/SM chip-wide cap) is what bounds the narrow output convolutions and sits at ~80 %
+// for the paired tower kernel.  Activations and weights get separate rings: an activation stage is consumed
+// by three weight stages (dy = 0,1,2).
+// ---------------------------------------------------------------------------------------------------
+constexpr int HALO_ROWS = TILE_H + 2;
+constexpr int HALO_A_HALF = HALO_ROWS * TILE_W * 128;   // one of (hi, lo): 20 KB
+constexpr int HALO_A_STAGE = 2 * HALO_A_HALF;
+constexpr int HALO_A_STAGES_MAX = 3;
+constexpr int HALO_ROW_BYTES = TILE_W * 128;            // 2048 B per staged pixel row
+constexpr int HALO_SMEM_BUDGET = 226 * 1024;
+
+template <int BN>
+struct CfgH {
+  static constexpr int B_HALF = BN * 128;
+  static constexpr int B_STAGE = 2 * B_HALF;
+  // An activation stage is held for three taps.  Narrow convolutions retire a tap in a few hundred cycles, less
+  // than the L2 round trip, so they need a third activation stage; the 256-wide ones (1.5k cycles per tap) do not.
+  static constexpr int A_STAGES = BN <= 128 ? 3 : 2;
+  static constexpr int B_STAGES_RAW = (HALO_SMEM_BUDGET - 1024 - A_STAGES * HALO_A_STAGE) / B_STAGE;
+  static constexpr int B_STAGES = B_STAGES_RAW > 8 ? 8 : B_STAGES_RAW;
+  static constexpr int SMEM_BYTES = 1024 + A_STAGES * HALO_A_STAGE + B_STAGES * B_STAGE;
+  static_assert(B_STAGES >= 2, "weight ring too shallow");
+  static_assert(B_HALF % 1024 == 0, "weight tile must keep 1024-B (swizzle atom) alignment");
+};
+
+// CTA pairs (N = 256 across the pair): every CTA stages 128 weight rows per tap
+struct CfgH2 {
+  static constexpr int B_HALF = 128 * 128;
+  static constexpr int B_STAGE = 2 * B_HALF;
+  static constexpr int A_STAGES = 2;
+  static constexpr int B_STAGES = (HALO_SMEM_BUDGET - 1024 - A_STAGES * HALO_A_STAGE) / B_STAGE;
+  static constexpr int SMEM_BYTES = 1024 + A_STAGES * HALO_A_STAGE + B_STAGES * B_STAGE;
+  static_assert(B_STAGES >= 3, "weight ring too shallow");
 };
 
 // bias / ReLU / Philox dropout / store of one pixel row: NG groups of 16 accumulator columns from `sum`
@@ -266,10 +329,12 @@ __device__ __forceinline__ void tile_epilogue(const Params& P, const float (&sum
     }
 }
 
-template <int BN, int BK, int MODE>
+template <int BN, int BK, int MODE, bool HALO>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_constant__ Params P) {
   using C = Cfg<BN, BK>;
-  constexpr int STAGES = C::STAGES;
+  using CH = CfgH<BN>;
+  static_assert(!HALO || BK == 64, "row-halo staging needs 128-byte operand rows");
+  constexpr int STAGES = HALO ? CH::B_STAGES : C::STAGES;   // HALO: full/empty_bar track the WEIGHT ring
   // Accumulation is CHUNKED: the tensor core sums one chunk of the K loop (default: one 3x3 tap =
   // Cin channels) into a fresh TMEM accumulator; the epilogue warps add the chunk results in fp32
   // round-to-nearest in registers.  tcgen05 accumulates with truncation, so a single 2304-long chain
@@ -280,6 +345,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t afull_bar[HALO_A_STAGES_MAX];   // HALO: activation ring
+  __shared__ __align__(8) uint64_t aempty_bar[HALO_A_STAGES_MAX];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
@@ -298,6 +365,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < HALO_A_STAGES_MAX; ++i) {
+      mbar_init(&afull_bar[i], 1);
+      mbar_init(&aempty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -323,6 +394,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
       // ================================ TMA producer ================================
       uint32_t stage = 0, phase = 0;
       bool ok = true;
+      if constexpr (HALO) {
+        uint32_t as = 0, aphase = 0;
+        for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
+          const int n = tile / tiles_per_map, r = tile % tiles_per_map;
+          const int y0 = (r / P.tiles_x) * TILE_H, x0 = (r % P.tiles_x) * TILE_W;
+          for (int cb = 0; cb < kb_per_tap && ok; ++cb) {
+            for (int dx = 0; dx < 3 && ok; ++dx) {
+              if (!mbar_wait(&aempty_bar[as], aphase ^ 1u, 5)) { ok = false; break; }
+              mbar_arrive_expect_tx(&afull_bar[as], (uint32_t)HALO_A_STAGE);
+              uint8_t* sa = smem + (size_t)as * HALO_A_STAGE;
+              tma_load_4d(&P.tm_a_hi, &afull_bar[as], sa, cb * 64, x0 + dx - 1, y0 - 1, n);
+              tma_load_4d(&P.tm_a_lo, &afull_bar[as], sa + HALO_A_HALF, cb * 64, x0 + dx - 1, y0 - 1, n);
+              if (++as == CH::A_STAGES) { as = 0; aphase ^= 1u; }
+              for (int dy = 0; dy < 3; ++dy) {
+                if (!mbar_wait(&empty_bar[stage], phase ^ 1u, 1)) { ok = false; break; }
+                mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)CH::B_STAGE);
+                uint8_t* sb = smem + CH::A_STAGES * HALO_A_STAGE + (size_t)stage * CH::B_STAGE;
+                const int kcol = (dy * 3 + dx) * P.Cin + cb * 64;
+                tma_load_2d(&P.tm_b_hi, &full_bar[stage], sb, kcol, 0);
+                tma_load_2d(&P.tm_b_lo, &full_bar[stage], sb + CH::B_HALF, kcol, 0);
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+              }
+            }
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
         const int n = tile / tiles_per_map, r = tile % tiles_per_map;
         const int y0 = (r / P.tiles_x) * TILE_H, x0 = (r % P.tiles_x) * TILE_W;
@@ -340,35 +437,75 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
           }
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ================================ MMA issuer ==================================
+    } else if (warp == 1) {
+      // ================================ MMA issuer (whole warp, one elected lane issues) ==============
+      const uint32_t leader = elect_one_sync();
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       bool ok = true;
+      if constexpr (HALO) {
+        uint32_t as = 0, aphase = 0;
+        for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
+          int dy = 0;                                   // unit order within a tile: (K-block, dx, dy), dy fastest
+          for (int c = 0; c < n_chunks && ok; ++c) {
+            if (!mbar_wait_all(&tempty_bar[acc], acc_phase ^ 1u, 2)) { ok = false; break; }
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+            for (int j = 0; j < kb_per_chunk; ++j) {
+              if (dy == 0 && !mbar_wait_all(&afull_bar[as], aphase, 6)) { ok = false; break; }
+              if (!mbar_wait_all(&full_bar[stage], phase, 3)) { ok = false; break; }
+              tcgen05_fence_after();
+              const uint32_t sa_hi = smem_base + as * HALO_A_STAGE + dy * HALO_ROW_BYTES;
+              const uint32_t sa_lo = sa_hi + HALO_A_HALF;
+              const uint32_t sb_hi = smem_base + CH::A_STAGES * HALO_A_STAGE + stage * CH::B_STAGE;
+              const uint32_t sb_lo = sb_hi + CH::B_HALF;
+              const uint64_t ah0 = make_smem_desc<128>(sa_hi), al0 = make_smem_desc<128>(sa_lo);
+              const uint64_t bh0 = make_smem_desc<128>(sb_hi), bl0 = make_smem_desc<128>(sb_lo);
+#pragma unroll
+              for (int k = 0; k < 64 / UMMA_K; ++k) {
+                const uint64_t koff = (uint64_t)(k * UMMA_K * 2) >> 4;   // descriptor address field is in 16-B units
+                const uint64_t ah = ah0 + koff, al = al0 + koff, bh = bh0 + koff, bl = bl0 + koff;
+                umma_f16(d_tmem, al, bh, C::IDESC, (j | k) != 0 ? 1u : 0u, leader);   // small terms first
+                umma_f16(d_tmem, ah, bl, C::IDESC, 1u, leader);
+                umma_f16(d_tmem, ah, bh, C::IDESC, 1u, leader);
+              }
+              umma_commit(&empty_bar[stage], leader);                          // weight slot free once these MMAs retire
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+              if (++dy == 3) {                                         // third row shift done: activation slot free
+                dy = 0;
+                umma_commit(&aempty_bar[as], leader);
+                if (++as == CH::A_STAGES) { as = 0; aphase ^= 1u; }
+              }
+              if (j == kb_per_chunk - 1) umma_commit(&tfull_bar[acc], leader);  // chunk complete -> epilogue warps
+            }
+            acc ^= 1u;
+            if (acc == 0) acc_phase ^= 1u;
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
         for (int c = 0; c < n_chunks && ok; ++c) {
-          if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 2)) { ok = false; break; }
+          if (!mbar_wait_all(&tempty_bar[acc], acc_phase ^ 1u, 2)) { ok = false; break; }
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
           for (int j = 0; j < kb_per_chunk; ++j) {
-            if (!mbar_wait(&full_bar[stage], phase, 3)) { ok = false; break; }
+            if (!mbar_wait_all(&full_bar[stage], phase, 3)) { ok = false; break; }
             tcgen05_fence_after();
             const uint32_t sa_hi = smem_base + stage * C::STAGE_BYTES;
             const uint32_t sa_lo = sa_hi + C::A_BYTES;
             const uint32_t sb_hi = sa_hi + 2 * C::A_BYTES;
             const uint32_t sb_lo = sb_hi + C::B_BYTES;
+            const uint64_t ah0 = make_smem_desc<C::ROW_BYTES>(sa_hi), al0 = make_smem_desc<C::ROW_BYTES>(sa_lo);
+            const uint64_t bh0 = make_smem_desc<C::ROW_BYTES>(sb_hi), bl0 = make_smem_desc<C::ROW_BYTES>(sb_lo);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint32_t koff = k * UMMA_K * 2;
-              const uint64_t ah = make_smem_desc<C::ROW_BYTES>(sa_hi + koff);
-              const uint64_t al = make_smem_desc<C::ROW_BYTES>(sa_lo + koff);
-              const uint64_t bh = make_smem_desc<C::ROW_BYTES>(sb_hi + koff);
-              const uint64_t bl = make_smem_desc<C::ROW_BYTES>(sb_lo + koff);
-              umma_f16(d_tmem, al, bh, C::IDESC, (j | k) != 0 ? 1u : 0u);   // small terms first
-              umma_f16(d_tmem, ah, bl, C::IDESC, 1u);
-              umma_f16(d_tmem, ah, bh, C::IDESC, 1u);
+              const uint64_t koff = (uint64_t)(k * UMMA_K * 2) >> 4;   // descriptor address field is in 16-B units
+              const uint64_t ah = ah0 + koff, al = al0 + koff, bh = bh0 + koff, bl = bl0 + koff;
+              umma_f16(d_tmem, al, bh, C::IDESC, (j | k) != 0 ? 1u : 0u, leader);   // small terms first
+              umma_f16(d_tmem, ah, bl, C::IDESC, 1u, leader);
+              umma_f16(d_tmem, ah, bh, C::IDESC, 1u, leader);
             }
-            umma_commit(&empty_bar[stage]);                          // frees the smem slot when the MMAs retire
-            if (j == kb_per_chunk - 1) umma_commit(&tfull_bar[acc]);  // chunk complete -> epilogue warps
+            umma_commit(&empty_bar[stage], leader);                          // frees the smem slot when the MMAs retire
+            if (j == kb_per_chunk - 1) umma_commit(&tfull_bar[acc], leader);  // chunk complete -> epilogue warps
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
           acc ^= 1u;
@@ -502,18 +639,23 @@ __device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
-__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                          uint32_t leader) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
 // arrives (once the issued MMAs retire) on the barrier at this smem offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3), "r"(leader) : "memory");
 }
 
 template <int BK>
@@ -529,14 +671,18 @@ struct Cfg2 {
   static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 };
 
-template <int BK, int MODE>
+template <int BK, int MODE, bool HALO>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc2(const __grid_constant__ Params P) {
   using C = Cfg2<BK>;
-  constexpr int STAGES = C::STAGES;
+  using CH = CfgH2;                                     // each CTA stages 128 of the 256 weight rows
+  static_assert(!HALO || BK == 64, "row-halo staging needs 128-byte operand rows");
+  constexpr int STAGES = HALO ? CH::B_STAGES : C::STAGES;   // HALO: full/empty_bar track the WEIGHT ring
   constexpr int COLS = 128, NG = 8, EPI_THREADS = 256;
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];    // used in the leader CTA only
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t afull_bar[HALO_A_STAGES_MAX];   // HALO: activation ring (full: leader only)
+  __shared__ __align__(8) uint64_t aempty_bar[HALO_A_STAGES_MAX];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];       // used in the leader CTA only
   __shared__ uint32_t tmem_base_s;
@@ -556,6 +702,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < HALO_A_STAGES_MAX; ++i) {
+      mbar_init(&afull_bar[i], 1);
+      mbar_init(&aempty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -583,6 +733,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
   if (warp == 0 && lane == 0) {
     // ================================ TMA producer (both CTAs) ================================
     uint32_t stage = 0, phase = 0;
+    [[maybe_unused]] uint32_t as = 0, aphase = 0;
     bool ok = true;
     for (int tp = pair0; tp < num_pairs && ok; tp += pair_step) {
       const int tile = 2 * tp + (int)rank;
@@ -590,6 +741,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
       const int n = tile < P.num_tiles ? tile / tiles_per_map : P.NB;
       const int r = tile < P.num_tiles ? tile % tiles_per_map : 0;
       const int y0 = (r / P.tiles_x) * TILE_H, x0 = (r % P.tiles_x) * TILE_W;
+      if constexpr (HALO) {
+        for (int cb = 0; cb < kb_per_tap && ok; ++cb) {
+          for (int dx = 0; dx < 3 && ok; ++dx) {
+            if (!mbar_wait(&aempty_bar[as], aphase ^ 1u, 15)) { ok = false; break; }
+            if (rank == 0) mbar_arrive_expect_tx(&afull_bar[as], 2u * (uint32_t)HALO_A_STAGE);
+            const uint32_t fa = mapa_cluster(smem_u32(&afull_bar[as]), 0);    // the leader's barriers
+            uint8_t* sa = smem + (size_t)as * HALO_A_STAGE;
+            tma2_load_4d(&P.tm_a_hi, fa, sa, cb * 64, x0 + dx - 1, y0 - 1, n);
+            tma2_load_4d(&P.tm_a_lo, fa, sa + HALO_A_HALF, cb * 64, x0 + dx - 1, y0 - 1, n);
+            if (++as == CH::A_STAGES) { as = 0; aphase ^= 1u; }
+            for (int dy = 0; dy < 3; ++dy) {
+              if (!mbar_wait(&empty_bar[stage], phase ^ 1u, 11)) { ok = false; break; }
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)CH::B_STAGE);
+              const uint32_t fb = mapa_cluster(smem_u32(&full_bar[stage]), 0);
+              uint8_t* sb = smem + CH::A_STAGES * HALO_A_STAGE + (size_t)stage * CH::B_STAGE;
+              const int kcol = (dy * 3 + dx) * P.Cin + cb * 64;
+              tma2_load_2d(&P.tm_b_hi, fb, sb, kcol, (int)rank * 128);
+              tma2_load_2d(&P.tm_b_lo, fb, sb + CH::B_HALF, kcol, (int)rank * 128);
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      } else
       for (int tap = 0; tap < 9 && ok; ++tap) {
         const int yy = y0 + tap / 3 - 1, xx = x0 + tap % 3 - 1;
         for (int cb = 0; cb < kb_per_tap; ++cb) {
@@ -605,35 +779,75 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
-    // ================================ MMA issuer (leader CTA) =================================
+  } else if (warp == 1 && rank == 0) {
+    // ================================ MMA issuer (leader CTA; whole warp, one elected lane issues) ====
+    const uint32_t leader = elect_one_sync();
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     bool ok = true;
+    if constexpr (HALO) {
+      uint32_t as = 0, aphase = 0;
+      for (int tp = pair0; tp < num_pairs && ok; tp += pair_step) {
+        int dy = 0;                                     // unit order within a tile: (K-block, dx, dy), dy fastest
+        for (int c = 0; c < n_chunks && ok; ++c) {
+          if (!mbar_wait_all(&tempty_bar[acc], acc_phase ^ 1u, 12)) { ok = false; break; }
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+          for (int j = 0; j < kb_per_chunk; ++j) {
+            if (dy == 0 && !mbar_wait_all(&afull_bar[as], aphase, 16)) { ok = false; break; }
+            if (!mbar_wait_all(&full_bar[stage], phase, 13)) { ok = false; break; }
+            tcgen05_fence_after();
+            const uint32_t sa_hi = smem_base + as * HALO_A_STAGE + dy * HALO_ROW_BYTES;
+            const uint32_t sa_lo = sa_hi + HALO_A_HALF;
+            const uint32_t sb_hi = smem_base + CH::A_STAGES * HALO_A_STAGE + stage * CH::B_STAGE;
+            const uint32_t sb_lo = sb_hi + CH::B_HALF;
+            const uint64_t ah0 = make_smem_desc<128>(sa_hi), al0 = make_smem_desc<128>(sa_lo);
+            const uint64_t bh0 = make_smem_desc<128>(sb_hi), bl0 = make_smem_desc<128>(sb_lo);
+#pragma unroll
+            for (int k = 0; k < 64 / UMMA_K; ++k) {
+              const uint64_t koff = (uint64_t)(k * UMMA_K * 2) >> 4;   // descriptor address field is in 16-B units
+              const uint64_t ah = ah0 + koff, al = al0 + koff, bh = bh0 + koff, bl = bl0 + koff;
+              umma2_f16(d_tmem, al, bh, C::IDESC, (j | k) != 0 ? 1u : 0u, leader);
+              umma2_f16(d_tmem, ah, bl, C::IDESC, 1u, leader);
+              umma2_f16(d_tmem, ah, bh, C::IDESC, 1u, leader);
+            }
+            umma2_commit_mc(&empty_bar[stage], leader);                          // weight slot free in both CTAs
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            if (++dy == 3) {                                             // activation slot free in both CTAs
+              dy = 0;
+              umma2_commit_mc(&aempty_bar[as], leader);
+              if (++as == CH::A_STAGES) { as = 0; aphase ^= 1u; }
+            }
+            if (j == kb_per_chunk - 1) umma2_commit_mc(&tfull_bar[acc], leader);  // chunk complete in both CTAs
+          }
+          acc ^= 1u;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+      }
+    } else
     for (int tp = pair0; tp < num_pairs && ok; tp += pair_step) {
       for (int c = 0; c < n_chunks && ok; ++c) {
-        if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 12)) { ok = false; break; }
+        if (!mbar_wait_all(&tempty_bar[acc], acc_phase ^ 1u, 12)) { ok = false; break; }
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         for (int j = 0; j < kb_per_chunk; ++j) {
-          if (!mbar_wait(&full_bar[stage], phase, 13)) { ok = false; break; }
+          if (!mbar_wait_all(&full_bar[stage], phase, 13)) { ok = false; break; }
           tcgen05_fence_after();
           const uint32_t sa_hi = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sa_lo = sa_hi + C::A_BYTES;
           const uint32_t sb_hi = sa_hi + 2 * C::A_BYTES;
           const uint32_t sb_lo = sb_hi + C::B_BYTES;
+          const uint64_t ah0 = make_smem_desc<C::ROW_BYTES>(sa_hi), al0 = make_smem_desc<C::ROW_BYTES>(sa_lo);
+          const uint64_t bh0 = make_smem_desc<C::ROW_BYTES>(sb_hi), bl0 = make_smem_desc<C::ROW_BYTES>(sb_lo);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint32_t koff = k * UMMA_K * 2;
-            const uint64_t ah = make_smem_desc<C::ROW_BYTES>(sa_hi + koff);
-            const uint64_t al = make_smem_desc<C::ROW_BYTES>(sa_lo + koff);
-            const uint64_t bh = make_smem_desc<C::ROW_BYTES>(sb_hi + koff);
-            const uint64_t bl = make_smem_desc<C::ROW_BYTES>(sb_lo + koff);
-            umma2_f16(d_tmem, al, bh, C::IDESC, (j | k) != 0 ? 1u : 0u);
-            umma2_f16(d_tmem, ah, bl, C::IDESC, 1u);
-            umma2_f16(d_tmem, ah, bh, C::IDESC, 1u);
+            const uint64_t koff = (uint64_t)(k * UMMA_K * 2) >> 4;   // descriptor address field is in 16-B units
+            const uint64_t ah = ah0 + koff, al = al0 + koff, bh = bh0 + koff, bl = bl0 + koff;
+            umma2_f16(d_tmem, al, bh, C::IDESC, (j | k) != 0 ? 1u : 0u, leader);
+            umma2_f16(d_tmem, ah, bl, C::IDESC, 1u, leader);
+            umma2_f16(d_tmem, ah, bh, C::IDESC, 1u, leader);
           }
-          umma2_commit_mc(&empty_bar[stage]);                          // frees the slot in both CTAs
-          if (j == kb_per_chunk - 1) umma2_commit_mc(&tfull_bar[acc]);  // chunk complete in both CTAs
+          umma2_commit_mc(&empty_bar[stage], leader);                          // frees the slot in both CTAs
+          if (j == kb_per_chunk - 1) umma2_commit_mc(&tfull_bar[acc], leader);  // chunk complete in both CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         acc ^= 1u;
@@ -718,12 +932,13 @@ static PFN_tmapEncodeTiled get_encode() {
   return fn;
 }
 
-static int encode_act(CUtensorMap* tm, const void* base, int Cin, int W, int H, int NB, long long map_stride_elems, int BK) {
+static int encode_act(CUtensorMap* tm, const void* base, int Cin, int W, int H, int NB, long long map_stride_elems, int BK,
+                      int box_rows) {
   PFN_tmapEncodeTiled enc = get_encode();
   POD_REQUIRE(enc, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
   cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)map_stride_elems * 2};
-  cuuint32_t box[4] = {(cuuint32_t)BK, TILE_W, TILE_H, 1};
+  cuuint32_t box[4] = {(cuuint32_t)BK, TILE_W, (cuuint32_t)box_rows, 1};
   cuuint32_t est[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, est,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -746,50 +961,50 @@ static int encode_wt(CUtensorMap* tm, const void* base, int Ktot, int rows, int 
   return 0;
 }
 
-template <int BN, int BK, int MODE>
+template <int BN, int BK, int MODE, bool HALO>
 static int launch(const Params& P, cudaStream_t st) {
-  using C = Cfg<BN, BK>;
-  auto kern = k_conv3x3_tc<BN, BK, MODE>;
+  constexpr int SMEM = HALO ? CfgH<BN>::SMEM_BYTES : Cfg<BN, BK>::SMEM_BYTES;
+  auto kern = k_conv3x3_tc<BN, BK, MODE, HALO>;
   static bool configured = false;
   if (!configured) {
-    POD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    POD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
   const int grid = P.num_tiles < pod_num_sms() ? P.num_tiles : pod_num_sms();
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(P);
+  kern<<<grid, NUM_THREADS, SMEM, st>>>(P);
   POD_LAUNCH_CHECK();
   return 0;
 }
 
-template <int BK, int MODE>
+template <int BK, int MODE, bool HALO>
 static int launch2(const Params& P, cudaStream_t st) {
-  using C = Cfg2<BK>;
-  auto kern = k_conv3x3_tc2<BK, MODE>;
+  constexpr int SMEM = HALO ? CfgH2::SMEM_BYTES : Cfg2<BK>::SMEM_BYTES;
+  auto kern = k_conv3x3_tc2<BK, MODE, HALO>;
   static bool configured = false;
   if (!configured) {
-    POD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    POD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
   const int pairs = (P.num_tiles + 1) / 2;
   const int max_pairs = pod_num_sms() / 2;
   const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(P);
+  kern<<<grid, NUM_THREADS, SMEM, st>>>(P);
   POD_LAUNCH_CHECK();
   return 0;
 }
 
 static int g_tc_pair = 1;   // 1: 256-channel convs run on CTA pairs (cta_group::2); 0: single-CTA kernel
 
-template <int BK, int MODE>
+template <int BK, int MODE, bool HALO>
 static int dispatch_bn(const Params& P, cudaStream_t st) {
-  if (P.Cout_pad == 256 && g_tc_pair) return launch2<BK, MODE>(P, st);
+  if (P.Cout_pad == 256 && g_tc_pair) return launch2<BK, MODE, HALO>(P, st);
   switch (P.Cout_pad) {
-    case 256: return launch<256, BK, MODE>(P, st);
-    case 128: return launch<128, BK, MODE>(P, st);
-    case 96: return launch<96, BK, MODE>(P, st);
-    case 80: return launch<80, BK, MODE>(P, st);
-    case 64: return launch<64, BK, MODE>(P, st);
-    case 48: return launch<48, BK, MODE>(P, st);
+    case 256: return launch<256, BK, MODE, HALO>(P, st);
+    case 128: return launch<128, BK, MODE, HALO>(P, st);
+    case 96: return launch<96, BK, MODE, HALO>(P, st);
+    case 80: return launch<80, BK, MODE, HALO>(P, st);
+    case 64: return launch<64, BK, MODE, HALO>(P, st);
+    case 48: return launch<48, BK, MODE, HALO>(P, st);
     default: break;
   }
   pod_set_error("pod_conv3x3_tc: unsupported Cout_pad %d (supported: 48,64,80,96,128,256)", P.Cout_pad);
@@ -798,6 +1013,7 @@ static int dispatch_bn(const Params& P, cudaStream_t st) {
 
 }  // namespace tc
 
+static int g_tc_halo = 1;     // 1: row-halo staging (K-block 64 only): one 10-row activation box serves three taps
 static int g_tc_bk = 64;      // K-block (channels per pipeline stage): 64 -> SWIZZLE_128B (default), 32 -> SWIZZLE_64B
 static int g_tc_taps = 1;     // taps per accumulation chunk (1, 3 or 9)
 static int g_tc_chunk_kb = 6; // if > 0: K-blocks per accumulation chunk (must divide 9*Cin/K-block); overrides taps.
@@ -806,6 +1022,11 @@ static int g_tc_chunk_kb = 6; // if > 0: K-blocks per accumulation chunk (must d
 extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_chunk_kblocks(int kb) {
   POD_REQUIRE(kb >= 0, "pod_conv3x3_tc_set_chunk_kblocks: must be >= 0");
   g_tc_chunk_kb = kb;
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_halo(int on) {
+  g_tc_halo = on ? 1 : 0;
   return 0;
 }
 
@@ -840,9 +1061,11 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   Params P;
   memset(&P, 0, sizeof(P));
   const int BK = g_tc_bk;
+  const bool halo = g_tc_halo && BK == 64;
+  const int box_rows = halo ? HALO_ROWS : TILE_H;
   int rc;
-  if ((rc = encode_act(&P.tm_a_hi, a->in_hi, a->Cin, a->W, a->H, a->NB, a->in_map_stride, BK))) return rc;
-  if ((rc = encode_act(&P.tm_a_lo, a->in_lo, a->Cin, a->W, a->H, a->NB, a->in_map_stride, BK))) return rc;
+  if ((rc = encode_act(&P.tm_a_hi, a->in_hi, a->Cin, a->W, a->H, a->NB, a->in_map_stride, BK, box_rows))) return rc;
+  if ((rc = encode_act(&P.tm_a_lo, a->in_lo, a->Cin, a->W, a->H, a->NB, a->in_map_stride, BK, box_rows))) return rc;
   // CTA pairs stage half of the 256 weight rows each
   const int b_box_rows = (a->Cout_pad == 256 && tc::g_tc_pair) ? 128 : a->Cout_pad;
   if ((rc = encode_wt(&P.tm_b_hi, a->w_hi, 9 * a->Cin, a->Cout_pad, BK, b_box_rows))) return rc;
@@ -895,10 +1118,14 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
     POD_REQUIRE(false, "pod_conv3x3_tc: unknown mode %d", a->mode);
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (BK == 64) {
-    return a->mode == POD_OUT_HIDDEN ? dispatch_bn<64, POD_OUT_HIDDEN>(P, st) : dispatch_bn<64, POD_OUT_RAW>(P, st);
+  if (halo) {
+    return a->mode == POD_OUT_HIDDEN ? dispatch_bn<64, POD_OUT_HIDDEN, true>(P, st) : dispatch_bn<64, POD_OUT_RAW, true>(P, st);
   }
-  return a->mode == POD_OUT_HIDDEN ? dispatch_bn<32, POD_OUT_HIDDEN>(P, st) : dispatch_bn<32, POD_OUT_RAW>(P, st);
+  if (BK == 64) {
+    return a->mode == POD_OUT_HIDDEN ? dispatch_bn<64, POD_OUT_HIDDEN, false>(P, st)
+                                     : dispatch_bn<64, POD_OUT_RAW, false>(P, st);
+  }
+  return a->mode == POD_OUT_HIDDEN ? dispatch_bn<32, POD_OUT_HIDDEN, false>(P, st) : dispatch_bn<32, POD_OUT_RAW, false>(P, st);
 }
 
 extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_status(int* status_host) {

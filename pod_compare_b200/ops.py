@@ -191,6 +191,10 @@ def set_conv_pair(on):
     check(_cabi.load_library().pod_conv3x3_tc_set_pair(int(bool(on))), "pod_conv3x3_tc_set_pair")
 
 
+def set_conv_halo(on):
+    check(_cabi.load_library().pod_conv3x3_tc_set_halo(int(bool(on))), "pod_conv3x3_tc_set_halo")
+
+
 def set_conv_chunk_kblocks(kb):
     check(_cabi.load_library().pod_conv3x3_tc_set_chunk_kblocks(int(kb)), "pod_conv3x3_tc_set_chunk_kblocks")
 

@@ -113,13 +113,17 @@ def test_simt_conv_vs_fp64(shape):
 
 
 @pytest.mark.parametrize("pair", [1, 0])
-@pytest.mark.parametrize("kblock", [32, 64])
+@pytest.mark.parametrize("staging", ["halo64", "tap64", "tap32"])
 @pytest.mark.parametrize("shape", CONV_SHAPES)
-def test_tc_conv_raw_vs_fp64(shape, kblock, pair):
+def test_tc_conv_raw_vs_fp64(shape, staging, pair):
+    """Every operand-staging variant of the tcgen05 kernel: row-halo boxes (default; one 10-row box serves three
+    taps), one box per tap with K-block 64, one box per tap with K-block 32."""
     NB, Cin, H, W, Cout = shape
     if pair == 0 and Cout != 256:
         pytest.skip("single-CTA / paired choice only exists for 256 output channels")
+    kblock = 32 if staging == "tap32" else 64
     ops.set_conv_kblock(kblock)
+    ops.set_conv_halo(staging == "halo64")
     ops.set_conv_pair(pair)
     try:
         g = torch.Generator().manual_seed(4)
@@ -135,6 +139,7 @@ def test_tc_conv_raw_vs_fp64(shape, kblock, pair):
         assert err < 1e-5
     finally:
         ops.set_conv_kblock(64)
+        ops.set_conv_halo(1)
         ops.set_conv_pair(1)
 
 
@@ -160,7 +165,16 @@ def test_tc_conv_chunked_accumulation_is_more_accurate():
     assert err[1] < err[9]
 
 
-def test_tc_conv_hidden_dropout_and_strided_input():
+@pytest.mark.parametrize("halo", [1, 0])
+def test_tc_conv_hidden_dropout_and_strided_input(halo):
+    ops.set_conv_halo(halo)
+    try:
+        _hidden_dropout_and_strided_input()
+    finally:
+        ops.set_conv_halo(1)
+
+
+def _hidden_dropout_and_strided_input():
     g = torch.Generator().manual_seed(5)
     NB, H, W = 4, 10, 18
     x = torch.randn((NB, 256, H, W), generator=g)
