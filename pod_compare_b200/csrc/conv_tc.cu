@@ -339,6 +339,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
   // Cin channels) into a fresh TMEM accumulator; the epilogue warps add the chunk results in fp32
   // round-to-nearest in registers.  tcgen05 accumulates with truncation, so a single 2304-long chain
   // drifts by ~2e-5 relative; per-tap chains keep the head within ~2e-6 of the fp32 reference.
+  // N-stacking (BN <= 128): the hi and lo weight tiles of a stage are adjacent in shared memory, so ONE MMA with
+  // N = 2*BN computes hi*hi' into columns [0,BN) and hi*lo' into [BN,2BN); a second MMA (N = BN) adds lo*hi' into
+  // [0,BN).  Two instructions and two reads of the 128-row activation operand per K-step instead of three; the
+  // narrow convolutions are bound by exactly those shared-memory operand reads.  The epilogue adds the two halves.
+  constexpr bool STACK = BN <= 128;
+  constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   constexpr int COLS = BN == 256 ? 128 : BN;          // accumulator columns owned by one epilogue thread
   constexpr int EPI_THREADS = BN == 256 ? 256 : 128;  // BN=256: 8 epilogue warps (2 column halves), else 4
   constexpr int NG = COLS / 16;
@@ -464,9 +470,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
               for (int k = 0; k < 64 / UMMA_K; ++k) {
                 const uint64_t koff = (uint64_t)(k * UMMA_K * 2) >> 4;   // descriptor address field is in 16-B units
                 const uint64_t ah = ah0 + koff, al = al0 + koff, bh = bh0 + koff, bl = bl0 + koff;
-                umma_f16(d_tmem, al, bh, C::IDESC, (j | k) != 0 ? 1u : 0u, leader);   // small terms first
-                umma_f16(d_tmem, ah, bl, C::IDESC, 1u, leader);
-                umma_f16(d_tmem, ah, bh, C::IDESC, 1u, leader);
+                if constexpr (STACK) {
+                  umma_f16(d_tmem, ah, bh, IDESC2, (j | k) != 0 ? 1u : 0u, leader);   // [hi*hi' | hi*lo'], N = 2*BN
+                  umma_f16(d_tmem, al, bh, C::IDESC, 1u, leader);                     // + lo*hi' into [0,BN)
+                } else {
+                  umma_f16(d_tmem, al, bh, C::IDESC, (j | k) != 0 ? 1u : 0u, leader);   // small terms first
+                  umma_f16(d_tmem, ah, bl, C::IDESC, 1u, leader);
+                  umma_f16(d_tmem, ah, bh, C::IDESC, 1u, leader);
+                }
               }
               umma_commit(&empty_bar[stage], leader);                          // weight slot free once these MMAs retire
               if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -500,9 +511,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t koff = (uint64_t)(k * UMMA_K * 2) >> 4;   // descriptor address field is in 16-B units
               const uint64_t ah = ah0 + koff, al = al0 + koff, bh = bh0 + koff, bl = bl0 + koff;
-              umma_f16(d_tmem, al, bh, C::IDESC, (j | k) != 0 ? 1u : 0u, leader);   // small terms first
-              umma_f16(d_tmem, ah, bl, C::IDESC, 1u, leader);
-              umma_f16(d_tmem, ah, bh, C::IDESC, 1u, leader);
+              if constexpr (STACK) {
+                umma_f16(d_tmem, ah, bh, IDESC2, (j | k) != 0 ? 1u : 0u, leader);   // [hi*hi' | hi*lo'], N = 2*BN
+                umma_f16(d_tmem, al, bh, C::IDESC, 1u, leader);                     // + lo*hi' into [0,BN)
+              } else {
+                umma_f16(d_tmem, al, bh, C::IDESC, (j | k) != 0 ? 1u : 0u, leader);   // small terms first
+                umma_f16(d_tmem, ah, bl, C::IDESC, 1u, leader);
+                umma_f16(d_tmem, ah, bh, C::IDESC, 1u, leader);
+              }
             }
             umma_commit(&empty_bar[stage], leader);                          // frees the smem slot when the MMAs retire
             if (j == kb_per_chunk - 1) umma_commit(&tfull_bar[acc], leader);  // chunk complete -> epilogue warps
@@ -539,7 +555,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
           tcgen05_fence_after();
           const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_COLS + col0;
           if (!P.dbg_skip_ld) {
-            if (NG % 4 == 0) {
+            if constexpr (STACK) {
+              // columns [0,BN): hi*hi' + lo*hi'; columns [BN,2BN): hi*lo'
+#pragma unroll
+              for (int g = 0; g < NG; ++g) {
+                uint32_t r0[16], r1[16];
+                tmem_ld16(trow + g * 16, r0);
+                tmem_ld16(trow + BN + g * 16, r1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  sum[g * 16 + i] = __fadd_rn(sum[g * 16 + i], __fadd_rn(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+              }
+            } else if (NG % 4 == 0) {
 #pragma unroll
               for (int g = 0; g < NG; g += 4) {
                 uint32_t r0[32], r1[32];
@@ -1013,7 +1041,8 @@ static int dispatch_bn(const Params& P, cudaStream_t st) {
 
 }  // namespace tc
 
-static int g_tc_halo = 1;     // 1: row-halo staging (K-block 64 only): one 10-row activation box serves three taps
+static int g_tc_halo = 0;     // 1: row-halo staging (K-block 64 only): one 10-row activation box serves three taps.
+                              // Off by default: measured equal on the narrow convs and ~1 % slower on the tower
 static int g_tc_bk = 64;      // K-block (channels per pipeline stage): 64 -> SWIZZLE_128B (default), 32 -> SWIZZLE_64B
 static int g_tc_taps = 1;     // taps per accumulation chunk (1, 3 or 9)
 static int g_tc_chunk_kb = 6; // if > 0: K-blocks per accumulation chunk (must divide 9*Cin/K-block); overrides taps.

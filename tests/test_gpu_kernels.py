@@ -116,8 +116,8 @@ def test_simt_conv_vs_fp64(shape):
 @pytest.mark.parametrize("staging", ["halo64", "tap64", "tap32"])
 @pytest.mark.parametrize("shape", CONV_SHAPES)
 def test_tc_conv_raw_vs_fp64(shape, staging, pair):
-    """Every operand-staging variant of the tcgen05 kernel: row-halo boxes (default; one 10-row box serves three
-    taps), one box per tap with K-block 64, one box per tap with K-block 32."""
+    """Every operand-staging variant of the tcgen05 kernel: row-halo boxes (one 10-row box serves three taps),
+    one box per tap with K-block 64 (default), one box per tap with K-block 32."""
     NB, Cin, H, W, Cout = shape
     if pair == 0 and Cout != 256:
         pytest.skip("single-CTA / paired choice only exists for 256 output channels")
@@ -139,7 +139,7 @@ def test_tc_conv_raw_vs_fp64(shape, staging, pair):
         assert err < 1e-5
     finally:
         ops.set_conv_kblock(64)
-        ops.set_conv_halo(1)
+        ops.set_conv_halo(0)
         ops.set_conv_pair(1)
 
 
@@ -171,7 +171,7 @@ def test_tc_conv_hidden_dropout_and_strided_input(halo):
     try:
         _hidden_dropout_and_strided_input()
     finally:
-        ops.set_conv_halo(1)
+        ops.set_conv_halo(0)
 
 
 def _hidden_dropout_and_strided_input():

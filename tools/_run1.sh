@@ -1,3 +1,3 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:^k_conv3x3_tc$' -c 3 -o gpurun_out/out_conv_v2 python bench.py --batch 2 --chunk 2 --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_out2.log 2>&1
-tail -2 gpurun_out/ncu_out2.log | cut -c1-300
+( timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 ) > gpurun_out/t_full.log; cat gpurun_out/t_full.log
+timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -2
