@@ -81,7 +81,10 @@ def workload_config(args, world):
             "global_batch": args.batch * world, "batch_per_gpu": args.batch, "mc_samples": args.n_mc,
             "image": "%dx%d" % (WIDTH, HEIGHT), "chunk_images": args.chunk,
             "parallelism": "image-sharded dp%d + NCCL all-gather of detections" % world,
-            "l2": "working set per step (tens of GB of activations) far exceeds the 126 MB L2; no flush needed"}
+            "l2": "working set per step (tens of GB of activations) far exceeds the 126 MB L2; no flush needed",
+            "unread_outputs": ("evaluated" if getattr(args, "keep_unread", False) else
+                               "left out: box_cls / box_cls_var / box_reg_var of the last sample are never read by the "
+                               "reference (probabilistic_inference.py:216-267); detections are bit-identical either way")}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -194,6 +197,9 @@ def main():
                     help="mc_pre = the headline metric (BASELINE configs[2]); the others are side measurements")
     ap.add_argument("--kblock", type=int, default=0)
     ap.add_argument("--pair", type=int, default=-1, help="1/0: force CTA-pair (cta_group::2) / single-CTA tower convs")
+    ap.add_argument("--keep-unread", action="store_true",
+                    help="also evaluate the last sample's class / variance tower passes, whose outputs the reference "
+                         "computes but never reads (default: left out, results identical)")
     ap.add_argument("--halo", type=int, default=-1, help="1/0: row-halo activation staging on / one TMA box per tap")
     ap.add_argument("--chunk-taps", type=int, default=0, help="taps per accumulation chunk (1, 3, 9)")
     ap.add_argument("--chunk-kblocks", type=int, default=0, help="K-blocks per accumulation chunk (overrides --chunk-taps)")
@@ -230,6 +236,7 @@ def main():
     sds = [S.make_head_state_dict(1000 * e, num_classes=7, use_dropout=m.use_dropout, cls_var=m.compute_cls_var,
                                   bbox_cov=m.compute_bbox_cov) for e in range(members)]
     pred.load_weight_sets(sds if members > 1 else sds[0])
+    pred.skip_unread_outputs = not args.keep_unread
     B = args.batch
     # synthetic FPN features of this rank's images (weak scaling: B images per GPU)
     img0 = rank * B

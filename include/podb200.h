@@ -79,9 +79,11 @@ typedef struct pod_dropout {
 
 /* MC-dropout replication of the (mask-independent) first tower layer, SURVEY Q2:
  * x (NB_in, H*W, C) fp32 post-ReLU  ->  NB_in*samples*passes masked, rescaled, split copies.
- * Replaces the first nn.Dropout of every tower evaluation (probabilistic_retinanet.py:422-424,518-523). */
+ * Replaces the first nn.Dropout of every tower evaluation (probabilistic_retinanet.py:422-424,518-523).
+ * live_reps (0 = all): only the first live_reps of the samples*passes copies of every image are written
+ * (see pod_conv_args.map_live). */
 int pod_mask_expand_split(const float* x, int NB_in, int HW, int C, const pod_dropout* d, float scale,
-                          void* dst_hi, void* dst_lo, void* stream);
+                          void* dst_hi, void* dst_lo, int live_reps, void* stream);
 
 /* ---- the head convolutions (probabilistic_retinanet.py:401-441,458-484,517-523) -------------
  * 3x3 / stride 1 / pad 1 convolution over NB channels-last maps as an implicit GEMM on the
@@ -124,6 +126,13 @@ typedef struct pod_conv_args {
   int split_col;
   int64_t out2_map_stride;
   int64_t out2_pixel_stride;
+  /* Optional live-map selection (0 = every map): the NB maps come in groups of map_group (one image's samples x
+   * passes) and only the first map_live maps of each group are evaluated; the others' outputs are left
+   * untouched.  Used to leave out the tower passes of the last MC sample / ensemble member, whose class logits
+   * and variance outputs the reference computes but never reads (probabilistic_inference.py:216-267: the sample
+   * "mean" runs over range(len-1); only box_delta of the last sample is used, :326-331). */
+  int map_group;
+  int map_live;
 } pod_conv_args;
 int pod_conv3x3_tc(const pod_conv_args* a, void* stream);
 /* Channels per pipeline stage of the tcgen05 kernel: 64 (SWIZZLE_128B operand tiles, default) or

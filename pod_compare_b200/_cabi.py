@@ -38,7 +38,7 @@ class ConvArgs(C.Structure):
                 ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_scale", C.c_float), ("out_f32", C.c_void_p),
                 ("out_map_stride", C.c_int64), ("out_pixel_stride", C.c_int64), ("drop", Dropout),
                 ("out2_f32", C.c_void_p), ("split_col", C.c_int), ("out2_map_stride", C.c_int64),
-                ("out2_pixel_stride", C.c_int64)]
+                ("out2_pixel_stride", C.c_int64), ("map_group", C.c_int), ("map_live", C.c_int)]
 
 
 class DecodeArgs(C.Structure):
@@ -104,7 +104,7 @@ def load_library():
     lib.pod_nchw_to_nhwc_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.pod_pack_conv_weight.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pod_pack_conv_weight_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
-    lib.pod_mask_expand_split.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Dropout), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pod_mask_expand_split.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Dropout), C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.pod_conv3x3_tc.argtypes = [C.POINTER(ConvArgs), C.c_void_p]
     lib.pod_conv3x3_tc_set_kblock.argtypes = [C.c_int]
     lib.pod_conv3x3_tc_set_chunk_taps.argtypes = [C.c_int]

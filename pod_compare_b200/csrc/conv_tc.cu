@@ -37,6 +37,7 @@ __device__ int g_status = 0;            // 0 ok; else code of the barrier wait t
 struct Params {
   CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
   int NB, H, W, Cin;
+  int map_group, map_live;   // logical map m -> physical map (m / map_live) * map_group + m % map_live
   int tiles_x, tiles_y, num_tiles;
   int Cout, Cout_pad;
   int relu;
@@ -57,6 +58,13 @@ struct Params {
   float drop_scale;
   PhiloxKey key;
 };
+
+// Live-map indirection: the maps of a launch come in groups of `map_group` (one group per image: its samples x
+// passes) of which only the first `map_live` are evaluated.  Lets the caller leave out the tower passes of the
+// last MC sample / ensemble member whose outputs the reference computes but never reads.
+__device__ __forceinline__ int physical_map(const Params& P, int m) {
+  return P.map_live == P.map_group ? m : (m / P.map_live) * P.map_group + m % P.map_live;
+}
 
 // ------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -403,7 +411,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
       if constexpr (HALO) {
         uint32_t as = 0, aphase = 0;
         for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
-          const int n = tile / tiles_per_map, r = tile % tiles_per_map;
+          const int n = physical_map(P, tile / tiles_per_map), r = tile % tiles_per_map;
           const int y0 = (r / P.tiles_x) * TILE_H, x0 = (r % P.tiles_x) * TILE_W;
           for (int cb = 0; cb < kb_per_tap && ok; ++cb) {
             for (int dx = 0; dx < 3 && ok; ++dx) {
@@ -427,7 +435,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
         }
       } else
       for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
-        const int n = tile / tiles_per_map, r = tile % tiles_per_map;
+        const int n = physical_map(P, tile / tiles_per_map), r = tile % tiles_per_map;
         const int y0 = (r / P.tiles_x) * TILE_H, x0 = (r % P.tiles_x) * TILE_W;
         for (int tap = 0; tap < 9 && ok; ++tap) {
           const int yy = y0 + tap / 3 - 1, xx = x0 + tap % 3 - 1;
@@ -540,7 +548,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
       uint32_t acc = 0, acc_phase = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
-        const int n = tile / tiles_per_map, r = tile % tiles_per_map;
+        const int n = physical_map(P, tile / tiles_per_map), r = tile % tiles_per_map;
         const int py = (r / P.tiles_x) * TILE_H + m / TILE_W, px = (r % P.tiles_x) * TILE_W + m % TILE_W;
         const bool valid = py < P.H && px < P.W;
         const int pixel = py * P.W + px;
@@ -766,7 +774,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
     for (int tp = pair0; tp < num_pairs && ok; tp += pair_step) {
       const int tile = 2 * tp + (int)rank;
       // the odd tail tile of the last pair loads map index NB: entirely out of bounds -> zero fill
-      const int n = tile < P.num_tiles ? tile / tiles_per_map : P.NB;
+      const int n = tile < P.num_tiles ? physical_map(P, tile / tiles_per_map) : P.NB;
       const int r = tile < P.num_tiles ? tile % tiles_per_map : 0;
       const int y0 = (r / P.tiles_x) * TILE_H, x0 = (r % P.tiles_x) * TILE_W;
       if constexpr (HALO) {
@@ -895,7 +903,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
     for (int tp = pair0; tp < num_pairs && ok; tp += pair_step) {
       const int tile = 2 * tp + (int)rank;
       const bool tile_ok = tile < P.num_tiles;
-      const int n = tile_ok ? tile / tiles_per_map : 0, r = tile_ok ? tile % tiles_per_map : 0;
+      const int n = tile_ok ? physical_map(P, tile / tiles_per_map) : 0, r = tile_ok ? tile % tiles_per_map : 0;
       const int py = (r / P.tiles_x) * TILE_H + m / TILE_W, px = (r % P.tiles_x) * TILE_W + m % TILE_W;
       const bool valid = tile_ok && py < P.H && px < P.W;
       const int pixel = py * P.W + px;
@@ -1102,7 +1110,16 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   P.NB = a->NB; P.H = a->H; P.W = a->W; P.Cin = a->Cin;
   P.tiles_x = (a->W + TILE_W - 1) / TILE_W;
   P.tiles_y = (a->H + TILE_H - 1) / TILE_H;
-  const long long nt = (long long)P.tiles_x * P.tiles_y * a->NB;
+  P.map_group = P.map_live = 1;
+  long long logical_maps = a->NB;
+  if (a->map_group > 0) {
+    POD_REQUIRE(a->NB % a->map_group == 0 && a->map_live > 0 && a->map_live <= a->map_group,
+                "pod_conv3x3_tc: map_group must divide NB and 0 < map_live <= map_group");
+    P.map_group = a->map_group;
+    P.map_live = a->map_live;
+    logical_maps = (long long)(a->NB / a->map_group) * a->map_live;
+  }
+  const long long nt = (long long)P.tiles_x * P.tiles_y * logical_maps;
   POD_REQUIRE(nt < (1ll << 31), "pod_conv3x3_tc: too many tiles");
   P.num_tiles = (int)nt;
   P.Cout = a->Cout; P.Cout_pad = a->Cout_pad;

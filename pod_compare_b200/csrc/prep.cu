@@ -102,7 +102,7 @@ extern "C" __attribute__((visibility("default"))) int pod_pack_conv_weight_f32(c
 // one thread = 8 consecutive channels (two Philox quads): 32-byte loads, 16-byte stores per copy
 __global__ void __launch_bounds__(256)
 k_mask_expand(const float* __restrict__ x, int64_t oct_per_map, int NB_in, pod_dropout d, float scale,
-              uint32_t thr, float dscale, PhiloxKey key, __half* __restrict__ hi, __half* __restrict__ lo) {
+              uint32_t thr, float dscale, PhiloxKey key, __half* __restrict__ hi, __half* __restrict__ lo, int live_reps) {
   const int reps = d.samples * d.passes;
   const int64_t total = oct_per_map * NB_in;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -111,8 +111,18 @@ k_mask_expand(const float* __restrict__ x, int64_t oct_per_map, int NB_in, pod_d
     const float4 v0 = __ldg(reinterpret_cast<const float4*>(x) + 2 * t);
     const float4 v1 = __ldg(reinterpret_cast<const float4*>(x) + 2 * t + 1);
     const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    // the kept value (and its fp16 split) does not depend on the sample: split once, select per copy
+    uint32_t kh[4], kl[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half h0, l0, h1, l1;
+      pod_split_h(v[2 * i] * dscale * scale, h0, l0);
+      pod_split_h(v[2 * i + 1] * dscale * scale, h1, l1);
+      kh[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      kl[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
     const uint32_t image = (uint32_t)(d.image0 + nb);
-    for (int r = 0; r < reps; ++r) {
+    for (int r = 0; r < live_reps; ++r) {
       const int sample = r / d.passes, pass = d.pass0 + r % d.passes;
       const uint32_t c1 = pod_dropout_c1(d.level, d.layer, d.tower, pass);
       const uint4 wa = philox4x32_10((uint32_t)(2 * o8), c1, (uint32_t)sample, image, key);
@@ -121,13 +131,9 @@ k_mask_expand(const float* __restrict__ x, int64_t oct_per_map, int NB_in, pod_d
       uint32_t ph[4], pl[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float a = w[2 * i] >= thr ? v[2 * i] * dscale : 0.f;
-        const float b = w[2 * i + 1] >= thr ? v[2 * i + 1] * dscale : 0.f;
-        __half h0, l0, h1, l1;
-        pod_split_h(a * scale, h0, l0);
-        pod_split_h(b * scale, h1, l1);
-        ph[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-        pl[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        const uint32_t m = (w[2 * i] >= thr ? 0x0000FFFFu : 0u) | (w[2 * i + 1] >= thr ? 0xFFFF0000u : 0u);
+        ph[i] = kh[i] & m;
+        pl[i] = kl[i] & m;
       }
       const int64_t oq = ((int64_t)nb * reps + r) * oct_per_map + o8;
       __stcs(reinterpret_cast<uint4*>(hi) + oq, make_uint4(ph[0], ph[1], ph[2], ph[3]));   // streaming: written once,
@@ -137,15 +143,17 @@ k_mask_expand(const float* __restrict__ x, int64_t oct_per_map, int NB_in, pod_d
 }
 
 extern "C" __attribute__((visibility("default"))) int pod_mask_expand_split(const float* x, int NB_in, int HW, int C, const pod_dropout* d, float scale,
-                                     void* dst_hi, void* dst_lo, void* stream) {
+                                     void* dst_hi, void* dst_lo, int live_reps, void* stream) {
   POD_REQUIRE(x && d && dst_hi && dst_lo && NB_in > 0 && HW > 0 && C > 0 && C % 8 == 0, "pod_mask_expand_split: bad args (C%%8)");
   POD_REQUIRE(d->samples > 0 && d->passes > 0 && d->p > 0.0 && d->p < 1.0, "pod_mask_expand_split: bad dropout spec");
+  POD_REQUIRE(live_reps >= 0 && live_reps <= d->samples * d->passes, "pod_mask_expand_split: live_reps out of range");
+  if (live_reps == 0) live_reps = d->samples * d->passes;
   const int64_t qpm = (int64_t)HW * C / 8;
   const int64_t total = qpm * NB_in;
   const int grid = (int)((total + 255) / 256 < (int64_t)pod_num_sms() * 16 ? (total + 255) / 256 : (int64_t)pod_num_sms() * 16);
   k_mask_expand<<<grid, 256, 0, (cudaStream_t)stream>>>(x, qpm, NB_in, *d, scale, pod_dropout_threshold(d->p),
                                                         pod_dropout_scale(d->p), pod_key(d->seed, POD_STREAM_DROPOUT),
-                                                        (__half*)dst_hi, (__half*)dst_lo);
+                                                        (__half*)dst_hi, (__half*)dst_lo, live_reps);
   POD_LAUNCH_CHECK();
   return 0;
 }
@@ -163,9 +171,49 @@ __global__ void k_sample_mean_q1(const float* __restrict__ x, int S, int64_t n, 
   }
 }
 
+// n % 4 == 0: four independent element chains per thread, 16-byte streaming loads issued eight samples at a time
+// (the adds of one element stay in the reference's order: ((x0 + x0) + x1) + ... + x_{S-2}).
+__global__ void __launch_bounds__(256)
+k_sample_mean_q1_v4(const float4* __restrict__ x, int S, int64_t n4, int64_t total4, float4* __restrict__ out) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total4; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = t / n4, e = t % n4;
+    const float4* p = x + b * S * n4 + e;
+    float4 acc = __ldcs(p);
+    int i = 0;
+    for (; i + 8 <= S - 1; i += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(p + (int64_t)(i + u) * n4);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc.x = __fadd_rn(acc.x, v[u].x); acc.y = __fadd_rn(acc.y, v[u].y);
+        acc.z = __fadd_rn(acc.z, v[u].z); acc.w = __fadd_rn(acc.w, v[u].w);
+      }
+    }
+    for (; i < S - 1; ++i) {
+      const float4 v = __ldcs(p + (int64_t)i * n4);
+      acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y);
+      acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+    }
+    if (S > 1) {
+      const float fs = (float)S;
+      acc = make_float4(__fdiv_rn(acc.x, fs), __fdiv_rn(acc.y, fs), __fdiv_rn(acc.z, fs), __fdiv_rn(acc.w, fs));
+    }
+    out[t] = acc;
+  }
+}
+
 extern "C" __attribute__((visibility("default"))) int pod_sample_mean_q1(const float* x, int B, int S, int64_t n, float* out, void* stream) {
   POD_REQUIRE(x && out && B > 0 && S > 0 && n > 0, "pod_sample_mean_q1: bad args");
   const int64_t total = (int64_t)B * n;
+  if (n % 4 == 0 && ((uintptr_t)x | (uintptr_t)out) % 16 == 0) {
+    const int64_t total4 = total / 4;
+    const int64_t want = (total4 + 255) / 256, cap = (int64_t)pod_num_sms() * 8;
+    k_sample_mean_q1_v4<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(x), S, n / 4, total4, reinterpret_cast<float4*>(out));
+    POD_LAUNCH_CHECK();
+    return 0;
+  }
   const int grid = (int)((total + 255) / 256 < (int64_t)pod_num_sms() * 32 ? (total + 255) / 256 : (int64_t)pod_num_sms() * 32);
   k_sample_mean_q1<<<grid, 256, 0, (cudaStream_t)stream>>>(x, S, n, total, out);
   POD_LAUNCH_CHECK();

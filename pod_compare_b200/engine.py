@@ -148,20 +148,30 @@ class HeadEngine:
             raise PodError("non-finite values in the input feature maps")
         return min(ACT_SCALE, ops.pow2_scale(amax, 32768.0)) if amax > 0 else ACT_SCALE
 
-    def _conv_hidden(self, src, NB, H, W, pcv, dst, drop, in_scale=ACT_SCALE):
+    def _conv_hidden(self, src, NB, H, W, pcv, dst, drop, in_scale=ACT_SCALE, map_group=0, map_live=0):
         ops.conv3x3_tc(src[0], src[1], in_scale, NB, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, pcv.cout,
-                       pcv.cout_pad, POD_OUT_HIDDEN, True, out_hi=dst[0], out_lo=dst[1], out_scale=ACT_SCALE, drop=drop)
+                       pcv.cout_pad, POD_OUT_HIDDEN, True, out_hi=dst[0], out_lo=dst[1], out_scale=ACT_SCALE, drop=drop,
+                       map_group=map_group, map_live=map_live)
 
-    def _conv_out(self, src, NB, H, W, blocks, out, out_offset, out_map_stride, in_map_stride=None, in_offset=0):
+    def _conv_out(self, src, NB, H, W, blocks, out, out_offset, out_map_stride, in_map_stride=None, in_offset=0,
+                  map_group=0, map_live=0):
         for pcv in blocks:
             ops.conv3x3_tc(src[0], src[1], ACT_SCALE, NB, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, pcv.cout,
                            pcv.cout_pad, POD_OUT_RAW, False, out_f32=out, out_offset=out_offset + pcv.col0,
                            out_map_stride=out_map_stride, out_pixel_stride=pcv.total_cout,
-                           in_map_stride=in_map_stride, in_offset=in_offset)
+                           in_map_stride=in_map_stride, in_offset=in_offset, map_group=map_group, map_live=map_live)
 
-    def head_mc(self, feats, n_mc, seed, image0):
+    def head_mc(self, feats, n_mc, seed, image0, skip_unread=False):
         """MC-dropout head loop: feats = list over levels of (B,256,H,W) fp32.
-        Returns raw per-sample outputs, each (B, N, R, D)."""
+        Returns raw per-sample outputs, each (B, N, R, D).
+
+        skip_unread: the reference's sample "mean" of box_cls / box_cls_var / box_reg_var runs over
+        range(len-1) (probabilistic_inference.py:216-267), so those three outputs of the LAST sample are
+        computed and never read; only its box_delta enters the epistemic covariance (:326-331).  With
+        skip_unread the tower passes that feed only those outputs are not evaluated (both passes of the class
+        tower and the variance pass of the box tower of sample N-1: 9 of the 12N+2 tower convolutions and 3 of
+        the 4N output convolutions); rows [:, N-1] of logits / logvar / regvar are then left unwritten.  Valid
+        only when the caller aggregates with the Q1 mean (pre-NMS modes), never for per-run inference."""
         pc, w = self.pc, self.ws[0]
         B = feats[0].shape[0]
         A, K = pc.num_anchors, pc.num_classes
@@ -195,29 +205,39 @@ class HeadEngine:
                 ops.conv3x3_tc(fhi, flo, fscale, B, H, W, 256, p0.w_hi, p0.w_lo, p0.w_scale, p0.bias, 256, 256,
                                POD_OUT_RAW, True, out_f32=c1, out_map_stride=HW * 256, out_pixel_stride=256)
                 d0 = ops.make_dropout(pc.dropout_rate, seed, image0, n_mc, t_passes, 0, tower, 0, lvl)
-                ops.mask_expand_split(c1[: B * HW * 256].view(B, HW, 256), d0, ACT_SCALE, act[0][0], act[0][1])
+                # maps of one image: sample-major, pass-minor; the unread ones (skip_unread) are its tail
+                grp = n_mc * t_passes
+                live = grp
+                if skip_unread and n_mc > 1:
+                    live = (n_mc - 1) * t_passes + (0 if tower == TOWER_CLS else 1)
+                ops.mask_expand_split(c1[: B * HW * 256].view(B, HW, 256), d0, ACT_SCALE, act[0][0], act[0][1], live_reps=live)
                 cur = 0
                 NB = B * n_mc * t_passes
                 for layer in range(1, len(tw)):
                     d = ops.make_dropout(pc.dropout_rate, seed, image0, n_mc, t_passes, 0, tower, layer, lvl)
-                    self._conv_hidden(act[cur], NB, H, W, tw[layer], act[cur ^ 1], d)
+                    self._conv_hidden(act[cur], NB, H, W, tw[layer], act[cur ^ 1], d, map_group=grp, map_live=live)
                     cur ^= 1
+                n_live = n_mc - 1 if (skip_unread and n_mc > 1) else n_mc        # samples whose mean/var heads are read
                 # output convs: pass-0 maps feed the mean head, pass-1 maps the variance head (Q2)
                 mean_pc, var_pc = (w.cls_score, w.cls_var) if tower == TOWER_CLS else (w.bbox_pred, w.bbox_cov)
                 mean_out = raw["logits"] if tower == TOWER_CLS else raw["deltas"]
                 D = mean_pc[0].total_cout // A
                 self._conv_out(act[cur], B * n_mc, H, W, mean_pc, mean_out, level_off[lvl] * D, R * D,
-                               in_map_stride=t_passes * HW * 256, in_offset=0)
+                               in_map_stride=t_passes * HW * 256, in_offset=0, map_group=n_mc,
+                               map_live=n_live if tower == TOWER_CLS else n_mc)
                 if has_var:
                     var_out = raw["logvar"] if tower == TOWER_CLS else raw["regvar"]
                     Dv = var_pc[0].total_cout // A
                     self._conv_out(act[cur], B * n_mc, H, W, var_pc, var_out, level_off[lvl] * Dv, R * Dv,
-                                   in_map_stride=2 * HW * 256, in_offset=HW * 256)
+                                   in_map_stride=2 * HW * 256, in_offset=HW * 256, map_group=n_mc, map_live=n_live)
         return raw, level_off
 
-    def head_eval(self, feats, members=None):
+    def head_eval(self, feats, members=None, skip_unread=False):
         """Deterministic head (eval mode): one forward per weight set; the reference's second tower
-        evaluation is identical to the first and is shared.  Returns (B, E, R, D) raw outputs."""
+        evaluation is identical to the first and is shared.  Returns (B, E, R, D) raw outputs.
+        skip_unread (see head_mc): the class tower of the LAST member feeds only outputs the Q1 mean never reads
+        and is not evaluated; rows [:, E-1] of logits / logvar stay unwritten (regvar is written: it shares the
+        fused box convolution with the deltas)."""
         pc = self.pc
         members = members if members is not None else list(range(len(self.ws)))
         E = len(members)
@@ -243,6 +263,8 @@ class HeadEngine:
             for e, mi in enumerate(members):
                 w = self.ws[mi]
                 for tower in (TOWER_CLS, TOWER_BOX):
+                    if skip_unread and E > 1 and e == E - 1 and tower == TOWER_CLS:
+                        continue
                     tw = w.towers[tower]
                     src, cur = (fhi, flo), 0
                     for layer in range(len(tw)):

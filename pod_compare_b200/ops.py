@@ -117,8 +117,9 @@ def pack_conv_weight_f32(w, cout_pad):
     return out
 
 
-def mask_expand_split(x, drop, scale, out_hi=None, out_lo=None):
-    """x (NB, HW, C) fp32 -> (NB*samples*passes, HW, C) fp16 split pair."""
+def mask_expand_split(x, drop, scale, out_hi=None, out_lo=None, live_reps=0):
+    """x (NB, HW, C) fp32 -> (NB*samples*passes, HW, C) fp16 split pair.  live_reps > 0: only the first
+    live_reps copies of every image are written (the others are never read, see conv3x3_tc map_live)."""
     lib = _cabi.require_device()
     _chk(x, torch.float32, "x")
     NB, HW, Cn = x.shape
@@ -130,11 +131,11 @@ def mask_expand_split(x, drop, scale, out_hi=None, out_lo=None):
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(lib.pod_mask_expand_split(ptr(x), NB, HW, Cn, C.byref(drop), scale, ptr(out_hi), ptr(out_lo), stream_ptr()),
-          "pod_mask_expand_split")
+    check(lib.pod_mask_expand_split(ptr(x), NB, HW, Cn, C.byref(drop), scale, ptr(out_hi), ptr(out_lo), int(live_reps),
+                                    stream_ptr()), "pod_mask_expand_split")
     if PROFILE is not None:
         e1.record()
-        PROFILE.append((e0, e1, 4.0 * NB * HW * Cn * (1 + reps), "mask_expand"))     # algorithmic bytes: 1 read + reps writes
+        PROFILE.append((e0, e1, 4.0 * NB * HW * Cn * (1 + (live_reps or reps)), "mask_expand"))   # 1 read + live writes
     _count()
     return out_hi, out_lo
 
@@ -142,7 +143,7 @@ def mask_expand_split(x, drop, scale, out_hi=None, out_lo=None):
 def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias, Cout, Cout_pad, mode, relu,
                out_hi=None, out_lo=None, out_scale=1.0, out_f32=None, out_map_stride=0, out_pixel_stride=0,
                drop=None, in_map_stride=None, in_offset=0, out_offset=0, out2_f32=None, out2_offset=0, split_col=0,
-               out2_map_stride=0, out2_pixel_stride=0):
+               out2_map_stride=0, out2_pixel_stride=0, map_group=0, map_live=0):
     """Raw-pointer launch of the tcgen05 convolution. `in_offset`/`out_offset` are ELEMENT offsets
     into in_hi/in_lo and out_f32."""
     lib = _cabi.require_device()
@@ -165,6 +166,7 @@ def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias,
     if out2_f32 is not None:
         a.out2_f32 = out2_f32.data_ptr() + out2_offset * 4
         a.split_col, a.out2_map_stride, a.out2_pixel_stride = split_col, out2_map_stride, out2_pixel_stride
+    a.map_group, a.map_live = int(map_group), int(map_live)
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -172,7 +174,8 @@ def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias,
     if PROFILE is not None:
         e1.record()
         tag = "tower256" if (Cout_pad == 256 and mode == POD_OUT_HIDDEN) else ("conv1" if Cout_pad == 256 else "out")
-        PROFILE.append((e0, e1, 2.0 * 9 * Cin * Cout * NB * H * W, tag))
+        maps = NB if not map_group else NB // map_group * map_live          # maps actually evaluated
+        PROFILE.append((e0, e1, 2.0 * 9 * Cin * Cout * maps * H * W, tag))
     _count()
 
 

@@ -76,6 +76,10 @@ class ProbabilisticPredictor:
         else:
             self.model.eval()
         self.backbone = None
+        # Pre-NMS aggregation never reads box_cls / box_cls_var / box_reg_var of the last sample or member
+        # (reference probabilistic_inference.py:216-267 loops over range(len-1)): the tower passes feeding
+        # only those outputs are left out.  Results are unchanged; set False to evaluate them anyway.
+        self.skip_unread_outputs = True
         self.rng_seed = int(self.cfg.SEED) if int(self.cfg.SEED) >= 0 else 0
         self.weight_sets = []
         self._engine = None
@@ -187,11 +191,12 @@ class ProbabilisticPredictor:
         if mode == 'ensembles':
             if len(self.weight_sets) != len(pi.ENSEMBLES.RANDOM_SEED_NUMS):
                 raise _cabi.PodError("ensembles mode needs one weight set per RANDOM_SEED_NUMS entry")
-            raw, level_off = eng.head_eval(feats)
+            raw, level_off = eng.head_eval(feats, skip_unread=self.skip_unread_outputs and not post_nms)
         elif self.mc_dropout_enabled and self.num_mc_dropout_runs > 1:
             if not self.model.use_dropout:
                 raise _cabi.PodError("MC_DROPOUT.ENABLE with DROPOUT_RATE == 0 is not supported")
-            raw, level_off = eng.head_mc(feats, self.num_mc_dropout_runs, seed, image0)
+            raw, level_off = eng.head_mc(feats, self.num_mc_dropout_runs, seed, image0,
+                                         skip_unread=self.skip_unread_outputs and not post_nms)
         else:
             raw, level_off = eng.head_eval(feats, members=[0])
         if post_nms:

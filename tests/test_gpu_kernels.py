@@ -59,11 +59,12 @@ def test_layout_and_split_roundtrip():
 
 def test_sample_mean_q1_bit_exact():
     g = torch.Generator().manual_seed(1)
-    for S_ in (1, 2, 5, 30):
-        x = torch.randn((3, S_, 1001), generator=g)
-        ref = O.quirk_mean([[x[:, s]] for s in range(S_)])[0] if S_ > 1 else x[:, 0]
-        got = ops.sample_mean_q1(x.cuda()).cpu()
-        assert torch.equal(got, ref), S_
+    for n in (1001, 1004):          # scalar path / 16-byte vector path (n % 4 == 0)
+        for S_ in (1, 2, 5, 9, 10, 18, 30):
+            x = torch.randn((3, S_, n), generator=g)
+            ref = O.quirk_mean([[x[:, s]] for s in range(S_)])[0] if S_ > 1 else x[:, 0]
+            got = ops.sample_mean_q1(x.cuda()).cpu()
+            assert torch.equal(got, ref), (n, S_)
 
 
 def test_mask_expand_matches_oracle():

@@ -367,6 +367,44 @@ def test_end_to_end_matches_oracle(name):
     _compare_path(res[0], cand, det, ref_final, ref_cand, ref_det, pp, mode in ("bayes_od", "anchor_statistics"))
 
 
+@pytest.mark.parametrize("name", ["mcdrop_pre_n4", "droponly_pre_n3", "bayesod_mc_n3", "ensembles_e3"])
+def test_unread_last_sample_outputs_are_skipped_without_changing_results(name):
+    """The reference never reads box_cls / box_cls_var / box_reg_var of the last MC sample / ensemble member
+    (probabilistic_inference.py:216-267 loops over range(len-1)).  Leaving out the tower passes that
+    feed only those outputs (predictor.skip_unread_outputs, default on) must give bit-identical detections, must
+    leave every output that IS read bit-identical, and must really skip the work (fewer maps evaluated)."""
+    opts, mode, n_mc, seeds, hw, out_hw, seed, img = C.CASES[name]
+    cfg, pp, sds, feats = _oracle_case(name)
+    feats3 = [torch.cat([f, f * 0.5, f * 1.5], 0) for f in feats]          # batch of 3: group indexing per image
+    out = {}
+    for skip in (True, False):
+        pred = build_predictor(cfg)
+        pred.load_weight_sets(sds if len(sds) > 1 else sds[0])
+        pred.skip_unread_outputs = skip
+        ops.PROFILE = []
+        try:
+            res, raw, cand, det = pred.infer_from_features(feats3, hw, out_hw, image0=img, seed=seed, return_raw=True)
+            torch.cuda.synchronize()
+            flop = sum(f for (_, _, f, tag) in ops.PROFILE if tag in ("tower256", "out"))
+        finally:
+            ops.PROFILE = None
+        out[skip] = (res, {k: (v.clone() if v is not None else None) for k, v in raw.items()}, flop)
+    (res_s, raw_s, flop_s), (res_f, raw_f, flop_f) = out[True], out[False]
+    assert flop_s < flop_f
+    S_ = raw_f["deltas"].shape[1]
+    assert torch.equal(raw_s["deltas"], raw_f["deltas"])                     # every sample's deltas are read (:326-331)
+    for k in ("logits", "logvar", "regvar"):
+        if raw_f[k] is not None:
+            assert torch.equal(raw_s[k][:, :S_ - 1], raw_f[k][:, :S_ - 1]), k
+    for a, b in zip(res_s, res_f):
+        assert len(a) == len(b)
+        assert torch.equal(a.pred_boxes.tensor, b.pred_boxes.tensor)
+        assert torch.equal(a.scores, b.scores)
+        assert torch.equal(a.pred_classes, b.pred_classes)
+        assert torch.equal(a.pred_cls_probs, b.pred_cls_probs)
+        assert torch.equal(a.pred_boxes_covariance, b.pred_boxes_covariance)
+
+
 def test_batched_equals_single_image():
     """B images in one call == B single-image calls (a batch is B independent problems)."""
     name = "mcdrop_pre_n4"

@@ -20,6 +20,7 @@ sds = [S.make_head_state_dict(s, num_classes=pp.num_classes, use_dropout=pp.use_
                               bbox_cov=pp.bbox_cov, cov_dims=pp.cov_dims) for s in seeds]
 feats = S.make_features(0, img, hw[0], hw[1])
 pred = build_predictor(cfg)
+pred.skip_unread_outputs = False      # the raw outputs of every sample are inspected below
 pred.load_weight_sets(sds if len(sds) > 1 else sds[0])
 res, raw, cand, det = pred.infer_from_features(feats, hw, out_hw, image0=img, seed=seed, return_raw=True)
 torch.set_num_threads(8)

@@ -28,6 +28,7 @@ drop = O.DropoutSource("philox", pp.dropout_rate, 7, 0)
 outs = [O.head_outputs(feats, O.unpack_head(sd, pp), pp, drop, sample=s) for s in range(N)]
 print("oracle: %.1f s, %d candidates, %d detections" % (time.time() - t0, ref_cand.boxes.shape[0], ref_final.boxes.shape[0]))
 pred = build_predictor(cfg)
+pred.skip_unread_outputs = False      # the raw outputs of every sample are inspected below
 pred.load_weight_sets(sd)
 ids_ref = {int(a): i for i, a in enumerate(ref_cand.anchor_ids)}
 for taps in (1, -6, -9, 3, 9):
