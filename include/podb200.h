@@ -145,6 +145,10 @@ int pod_conv3x3_tc_set_chunk_taps(int taps);
 /* Finer control: K-blocks per accumulation chunk (default 6 = 384 channels = 1.5 taps; 0 = use the taps
  * setting); ignored for a convolution whose K-block count it does not divide. */
 int pod_conv3x3_tc_set_chunk_kblocks(int kb);
+/* Weights-as-A kernel for RAW convolutions of <= 64 output channels (default on): the weight tile with its hi and
+ * lo halves stacked along M is the A operand and 256 pixels are the N operand, two full-size MMAs per K-step.
+ * Taken only when w_lo == w_hi + 64 rows (pod_pack_conv_weight into one buffer) and Cout_pad == 64. */
+int pod_conv3x3_tc_set_wt(int on);
 /* Row-halo activation staging (default off, K-block 64 only): one 10-row x 16-column TMA box per column shift
  * serves the three row-shifted taps through descriptor offsets, cutting activation bytes into the SM 2.4x.
  * Process-wide tuning knob; the K order of the accumulation differs (results agree to fp32 round-off). */

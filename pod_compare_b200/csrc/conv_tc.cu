@@ -969,12 +969,12 @@ static PFN_tmapEncodeTiled get_encode() {
 }
 
 static int encode_act(CUtensorMap* tm, const void* base, int Cin, int W, int H, int NB, long long map_stride_elems, int BK,
-                      int box_rows) {
+                      int box_rows, int box_cols = TILE_W) {
   PFN_tmapEncodeTiled enc = get_encode();
   POD_REQUIRE(enc, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
   cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)map_stride_elems * 2};
-  cuuint32_t box[4] = {(cuuint32_t)BK, TILE_W, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
   cuuint32_t est[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, est,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -1029,6 +1029,238 @@ static int launch2(const Params& P, cudaStream_t st) {
   return 0;
 }
 
+// =====================================================================================================
+// Weights-as-A variant for the narrow output convolutions (Cout <= 64, RAW mode).
+//
+// With pixels as the M operand a 63-channel head is an N=64 GEMM: every MMA re-reads the 4 KB activation operand
+// for 32 cycles of math and the tensor pipe idles on shared-memory operand fetch.  Here the roles
+// are swapped: A = the weight tile with its hi and lo parts STACKED along M (rows 0-63 = w_hi, 64-127 = w_lo; the
+// two packed halves are adjacent in global memory, so one TMA box fetches both), B = 256 pixels (16 x 16) of one of
+// (x_hi, x_lo).  Two full-size MMAs (M=128, N=256) per K-step
+//     D[0:64]   += w_hi . x_hi^T + w_hi . x_lo^T
+//     D[64:128] += w_lo . x_hi^T + w_lo . x_lo^T          (the lo.lo term is 2^-22, kept for free)
+// evaluate 256 pixels; the epilogue adds the two lane halves through shared memory once per tile.  D rows are
+// output channels and columns are pixels, so a warp stores 32 consecutive channels of one pixel: coalesced in the
+// permuted (pixel, A*K) output layout.
+// Rings: weight stages (16 KB) are consumed by two pixel stages (x_hi, x_lo; 32 KB each).
+// =====================================================================================================
+constexpr int WT_TILE = 16;                        // 16 x 16 pixel tile
+constexpr int WT_X_STAGE = 256 * 128;              // one of (hi, lo): 256 pixels x 64 channels
+constexpr int WT_W_STAGE = 128 * 128;              // [w_hi (64 rows); w_lo (64 rows)] x 64 channels
+constexpr int WT_X_STAGES = 4;
+constexpr int WT_W_STAGES = 3;
+constexpr int WT_XCHG = 2 * 64 * 64 * 4;           // lane-half exchange: 2 column halves x 64 columns x 64 rows fp32
+constexpr int WT_SMEM = 1024 + WT_X_STAGES * WT_X_STAGE + WT_W_STAGES * WT_W_STAGE + WT_XCHG;
+static_assert(WT_SMEM <= 227 * 1024, "weights-as-A kernel exceeds shared memory");
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_wt(const __grid_constant__ Params P) {
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr int COLS = 128, NG = 8, EPI_THREADS = 256;
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t xfull_bar[WT_X_STAGES];
+  __shared__ __align__(8) uint64_t xempty_bar[WT_X_STAGES];
+  __shared__ __align__(8) uint64_t wfull_bar[WT_W_STAGES];
+  __shared__ __align__(8) uint64_t wempty_bar[WT_W_STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  uint8_t* smem = smem_dyn + (smem_base - smem_u32(smem_dyn));
+  constexpr uint32_t W_OFF = WT_X_STAGES * WT_X_STAGE;
+  constexpr uint32_t XCHG_OFF = W_OFF + WT_W_STAGES * WT_W_STAGE;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.tm_a_hi);
+    tma_prefetch_desc(&P.tm_a_lo);
+    tma_prefetch_desc(&P.tm_b_hi);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < WT_X_STAGES; ++i) {
+      mbar_init(&xfull_bar[i], 1);
+      mbar_init(&xempty_bar[i], 1);
+    }
+    for (int i = 0; i < WT_W_STAGES; ++i) {
+      mbar_init(&wfull_bar[i], 1);
+      mbar_init(&wempty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], EPI_THREADS / 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int kb_per_tap = P.Cin / 64;
+  const int kb_total = 9 * kb_per_tap;
+  const int kb_per_chunk = P.kb_per_chunk;
+  const int n_chunks = kb_total / kb_per_chunk;
+  const int tiles_per_map = P.tiles_x * P.tiles_y;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0 && lane == 0) {
+      // ================================ TMA producer ================================
+      uint32_t xs = 0, xphase = 0, ws = 0, wphase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
+        const int n = physical_map(P, tile / tiles_per_map), r = tile % tiles_per_map;
+        const int y0 = (r / P.tiles_x) * WT_TILE, x0 = (r % P.tiles_x) * WT_TILE;
+        for (int tap = 0; tap < 9 && ok; ++tap) {
+          const int yy = y0 + tap / 3 - 1, xx = x0 + tap % 3 - 1;
+          for (int cb = 0; cb < kb_per_tap && ok; ++cb) {
+            if (!mbar_wait(&wempty_bar[ws], wphase ^ 1u, 21)) { ok = false; break; }
+            mbar_arrive_expect_tx(&wfull_bar[ws], (uint32_t)WT_W_STAGE);
+            tma_load_2d(&P.tm_b_hi, &wfull_bar[ws], smem + W_OFF + (size_t)ws * WT_W_STAGE, tap * P.Cin + cb * 64, 0);
+            if (++ws == WT_W_STAGES) { ws = 0; wphase ^= 1u; }
+            for (int part = 0; part < 2; ++part) {
+              if (!mbar_wait(&xempty_bar[xs], xphase ^ 1u, 22)) { ok = false; break; }
+              mbar_arrive_expect_tx(&xfull_bar[xs], (uint32_t)WT_X_STAGE);
+              tma_load_4d(part == 0 ? &P.tm_a_hi : &P.tm_a_lo, &xfull_bar[xs], smem + (size_t)xs * WT_X_STAGE, cb * 64, xx, yy, n);
+              if (++xs == WT_X_STAGES) { xs = 0; xphase ^= 1u; }
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ================================ MMA issuer (whole warp, one elected lane issues) ==============
+      const uint32_t leader = elect_one_sync();
+      uint32_t xs = 0, xphase = 0, ws = 0, wphase = 0, acc = 0, acc_phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
+        for (int c = 0; c < n_chunks && ok; ++c) {
+          if (!mbar_wait_all(&tempty_bar[acc], acc_phase ^ 1u, 23)) { ok = false; break; }
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+          for (int j = 0; j < kb_per_chunk && ok; ++j) {
+            if (!mbar_wait_all(&wfull_bar[ws], wphase, 24)) { ok = false; break; }
+            const uint64_t w0 = make_smem_desc<128>(smem_base + W_OFF + ws * WT_W_STAGE);
+            for (int part = 0; part < 2; ++part) {
+              if (!mbar_wait_all(&xfull_bar[xs], xphase, 25)) { ok = false; break; }
+              tcgen05_fence_after();
+              const uint64_t x0d = make_smem_desc<128>(smem_base + xs * WT_X_STAGE);
+#pragma unroll
+              for (int k = 0; k < 64 / UMMA_K; ++k) {
+                const uint64_t koff = (uint64_t)(k * UMMA_K * 2) >> 4;
+                umma_f16(d_tmem, w0 + koff, x0d + koff, IDESC, (j | part | k) != 0 ? 1u : 0u, leader);
+              }
+              umma_commit(&xempty_bar[xs], leader);
+              if (++xs == WT_X_STAGES) { xs = 0; xphase ^= 1u; }
+            }
+            umma_commit(&wempty_bar[ws], leader);
+            if (++ws == WT_W_STAGES) { ws = 0; wphase ^= 1u; }
+            if (j == kb_per_chunk - 1) umma_commit(&tfull_bar[acc], leader);
+          }
+          acc ^= 1u;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue ====================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int quad = warp & 3;               // TMEM lane quadrant: rows quad*32 .. +31 of D
+    const int half = (warp - 4) >> 2;        // column (pixel) half
+    const int col0 = half * COLS;
+    float* xchg = reinterpret_cast<float*>(smem + XCHG_OFF) + half * (64 * 64);
+    uint32_t acc = 0, acc_phase = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
+      const int n = physical_map(P, tile / tiles_per_map), r = tile % tiles_per_map;
+      const int y0 = (r / P.tiles_x) * WT_TILE, x0 = (r % P.tiles_x) * WT_TILE;
+      float sum[COLS];
+#pragma unroll
+      for (int i = 0; i < COLS; ++i) sum[i] = 0.f;
+      for (int c = 0; c < n_chunks; ++c) {
+        if (!warp_mbar_wait(&tfull_bar[acc], acc_phase, 26, lane)) { ok = false; break; }
+        tcgen05_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * ACC_COLS + col0;
+#pragma unroll
+        for (int g = 0; g < NG; g += 4) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(trow + g * 16, r0);
+          tmem_ld32(trow + (g + 2) * 16, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum[g * 16 + i] = __fadd_rn(sum[g * 16 + i], __uint_as_float(r0[i]));
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum[(g + 2) * 16 + i] = __fadd_rn(sum[(g + 2) * 16 + i], __uint_as_float(r1[i]));
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      if (!ok) break;
+      // rows 64-127 hold the w_lo products of the same output channels: hand them to rows 0-63, 64 columns a round
+#pragma unroll
+      for (int rd = 0; rd < 2; ++rd) {
+        if (quad >= 2) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) xchg[i * 64 + (quad - 2) * 32 + lane] = sum[rd * 64 + i];
+        }
+        named_bar_sync(1 + half, 128);
+        if (quad < 2) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) sum[rd * 64 + i] = __fadd_rn(sum[rd * 64 + i], xchg[i * 64 + quad * 32 + lane]);
+        }
+        named_bar_sync(1 + half, 128);
+      }
+      const int ch = quad * 32 + lane;
+      if (quad < 2 && ch < P.Cout) {
+        const float b = __ldg(P.bias + ch);
+        const long long pstride = P.out_pixel_stride;
+        // this thread's 128 columns are 8 rows x 16 columns of the pixel tile
+        float* o = P.out_f32 + (long long)n * P.out_map_stride + ch +
+                   ((long long)(y0 + half * (WT_TILE / 2)) * P.W + x0) * pstride;
+        const int rows_ok = P.H - (y0 + half * (WT_TILE / 2)), cols_ok = P.W - x0;
+#pragma unroll
+        for (int ty = 0; ty < WT_TILE / 2; ++ty) {
+          if (ty < rows_ok) {
+#pragma unroll
+            for (int tx = 0; tx < WT_TILE; ++tx) {
+              float v = fmaf(sum[ty * WT_TILE + tx], P.acc_scale, b);
+              if (P.relu) v = fmaxf(v, 0.f);
+              if (tx < cols_ok) o[tx * pstride] = v;
+            }
+          }
+          o += (long long)P.W * pstride;
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int launch_wt(const Params& P, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    POD_CUDA(cudaFuncSetAttribute(k_conv3x3_wt, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+    configured = true;
+  }
+  const int grid = P.num_tiles < pod_num_sms() ? P.num_tiles : pod_num_sms();
+  k_conv3x3_wt<<<grid, NUM_THREADS, WT_SMEM, st>>>(P);
+  POD_LAUNCH_CHECK();
+  return 0;
+}
+
 static int g_tc_pair = 1;   // 1: 256-channel convs run on CTA pairs (cta_group::2); 0: single-CTA kernel
 
 template <int BK, int MODE, bool HALO>
@@ -1049,6 +1281,7 @@ static int dispatch_bn(const Params& P, cudaStream_t st) {
 
 }  // namespace tc
 
+static int g_tc_wt = 1;       // 1: output convolutions of <= 64 channels run weights-as-A (k_conv3x3_wt)
 static int g_tc_halo = 0;     // 1: row-halo staging (K-block 64 only): one 10-row activation box serves three taps.
                               // Off by default: measured equal on the narrow convs and ~1 % slower on the tower
 static int g_tc_bk = 64;      // K-block (channels per pipeline stage): 64 -> SWIZZLE_128B (default), 32 -> SWIZZLE_64B
@@ -1059,6 +1292,11 @@ static int g_tc_chunk_kb = 6; // if > 0: K-blocks per accumulation chunk (must d
 extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_chunk_kblocks(int kb) {
   POD_REQUIRE(kb >= 0, "pod_conv3x3_tc_set_chunk_kblocks: must be >= 0");
   g_tc_chunk_kb = kb;
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_wt(int on) {
+  g_tc_wt = on ? 1 : 0;
   return 0;
 }
 
@@ -1098,6 +1336,41 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   Params P;
   memset(&P, 0, sizeof(P));
   const int BK = g_tc_bk;
+  // weights-as-A: RAW mode, <= 64 output channels, single destination, hi|lo weight halves adjacent (stacked along M)
+  const bool wt = g_tc_wt && BK == 64 && a->mode == POD_OUT_RAW && a->Cout_pad == 64 && a->out2_f32 == nullptr &&
+                  (const char*)a->w_lo == (const char*)a->w_hi + (size_t)64 * 9 * a->Cin * 2;
+  if (wt) {
+    POD_REQUIRE(a->out_f32 && a->out_pixel_stride >= a->Cout, "pod_conv3x3_tc: raw mode needs out_f32 / pixel stride >= Cout");
+    int rc;
+    if ((rc = encode_act(&P.tm_a_hi, a->in_hi, a->Cin, a->W, a->H, a->NB, a->in_map_stride, 64, WT_TILE, WT_TILE))) return rc;
+    if ((rc = encode_act(&P.tm_a_lo, a->in_lo, a->Cin, a->W, a->H, a->NB, a->in_map_stride, 64, WT_TILE, WT_TILE))) return rc;
+    if ((rc = encode_wt(&P.tm_b_hi, a->w_hi, 9 * a->Cin, 128, 64, 128))) return rc;
+    P.tm_b_lo = P.tm_b_hi;
+    P.NB = a->NB; P.H = a->H; P.W = a->W; P.Cin = a->Cin;
+    P.tiles_x = (a->W + WT_TILE - 1) / WT_TILE;
+    P.tiles_y = (a->H + WT_TILE - 1) / WT_TILE;
+    P.map_group = P.map_live = 1;
+    long long logical_maps = a->NB;
+    if (a->map_group > 0) {
+      POD_REQUIRE(a->NB % a->map_group == 0 && a->map_live > 0 && a->map_live <= a->map_group,
+                  "pod_conv3x3_tc: map_group must divide NB and 0 < map_live <= map_group");
+      P.map_group = a->map_group;
+      P.map_live = a->map_live;
+      logical_maps = (long long)(a->NB / a->map_group) * a->map_live;
+    }
+    const long long nt = (long long)P.tiles_x * P.tiles_y * logical_maps;
+    POD_REQUIRE(nt < (1ll << 31), "pod_conv3x3_tc: too many tiles");
+    P.num_tiles = (int)nt;
+    P.Cout = a->Cout; P.Cout_pad = a->Cout_pad;
+    P.relu = a->relu;
+    P.kb_per_chunk = g_tc_taps * (a->Cin / 64);
+    if (g_tc_chunk_kb > 0 && (9 * (a->Cin / 64)) % g_tc_chunk_kb == 0) P.kb_per_chunk = g_tc_chunk_kb;
+    P.acc_scale = 1.0f / (a->in_scale * a->w_scale);
+    P.bias = a->bias;
+    P.out_f32 = a->out_f32;
+    P.out_map_stride = a->out_map_stride; P.out_pixel_stride = a->out_pixel_stride;
+    return launch_wt(P, (cudaStream_t)stream);
+  }
   const bool halo = g_tc_halo && BK == 64;
   const int box_rows = halo ? HALO_ROWS : TILE_H;
   int rc;

@@ -30,7 +30,8 @@ TOWER_CLS, TOWER_BOX = 0, 1
 
 
 def _pad_cout(c):
-    for p in (48, 64, 80, 96, 128, 256):
+    # <= 64 channels always pad to 64: those convolutions run weights-as-A, whose cost does not depend on Cout
+    for p in (64, 80, 96, 128, 256):
         if c <= p:
             return p
     raise PodError("unsupported output channel count %d" % c)
@@ -48,10 +49,10 @@ class PackedConv:
     total_cout: int = 0    # output channels of the whole convolution
 
 
-def pack_conv(weight, bias, device):
+def pack_conv(weight, bias, device, cout_pad=None):
     w = weight.detach().to(device=device, dtype=torch.float32).contiguous()
     cout = w.shape[0]
-    cout_pad = _pad_cout(cout)
+    cout_pad = cout_pad or _pad_cout(cout)
     scale = ops.pow2_scale(float(w.abs().max()), 1024.0)
     hi, lo = ops.pack_conv_weight(w, cout_pad, scale)
     b = torch.zeros((cout_pad,), dtype=torch.float32, device=device)

@@ -100,8 +100,9 @@ def pack_conv_weight(w, cout_pad, scale):
     _chk(w, torch.float32, "w")
     cout, cin = w.shape[0], w.shape[1]
     assert tuple(w.shape[2:]) == (3, 3)
-    hi = torch.empty((cout_pad, 9 * cin), dtype=torch.float16, device=w.device)
-    lo = torch.empty_like(hi)
+    # one buffer, hi rows then lo rows: the weights-as-A kernel fetches the stacked [hi; lo] tile with one TMA box
+    both = torch.empty((2 * cout_pad, 9 * cin), dtype=torch.float16, device=w.device)
+    hi, lo = both[:cout_pad], both[cout_pad:]
     check(lib.pod_pack_conv_weight(ptr(w), cout, cin, cout_pad, scale, ptr(hi), ptr(lo), stream_ptr()), "pod_pack_conv_weight")
     _count()
     return hi, lo
@@ -192,6 +193,10 @@ def set_conv_kblock(bk):
 
 def set_conv_pair(on):
     check(_cabi.load_library().pod_conv3x3_tc_set_pair(int(bool(on))), "pod_conv3x3_tc_set_pair")
+
+
+def set_conv_wt(on):
+    check(_cabi.load_library().pod_conv3x3_tc_set_wt(int(bool(on))), "pod_conv3x3_tc_set_wt")
 
 
 def set_conv_halo(on):

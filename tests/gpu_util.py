@@ -14,11 +14,11 @@ def conv_ref64(x, w, b, relu):
     return torch.relu(y) if relu else y
 
 
-def tc_conv_raw(x_nchw, w, b, relu):
+def tc_conv_raw(x_nchw, w, b, relu, cout_pad=None):
     """x (NB,Cin,H,W) fp32 CPU -> (NB,Cout,H,W) fp32 CPU through the tcgen05 kernel (RAW mode)."""
     NB, Cin, H, W = x_nchw.shape
     hi, lo = ops.nchw_to_nhwc_split(x_nchw.cuda().contiguous(), ACT)
-    pcv = engine.pack_conv(w, b, "cuda")
+    pcv = engine.pack_conv(w, b, "cuda", cout_pad=cout_pad)
     out = torch.full((NB, H * W, pcv.cout), float("nan"), dtype=torch.float32, device="cuda")
     ops.conv3x3_tc(hi, lo, ACT, NB, H, W, Cin, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, pcv.cout, pcv.cout_pad,
                    POD_OUT_RAW, relu, out_f32=out, out_map_stride=H * W * pcv.cout, out_pixel_stride=pcv.cout)

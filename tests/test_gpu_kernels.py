@@ -144,6 +144,41 @@ def test_tc_conv_raw_vs_fp64(shape, staging, pair):
         ops.set_conv_pair(1)
 
 
+WT_SHAPES = [  # (NB, Cin, H, W, Cout): output convolutions of <= 64 channels run weights-as-A (16x16 pixel tiles)
+    (2, 256, 6, 10, 63),       # P7-like: one partial tile
+    (3, 256, 20, 40, 63),      # ragged in x and y, several maps
+    (1, 64, 17, 33, 40),       # one pixel past a tile in both directions, Cin=64
+    (2, 128, 9, 17, 64),       # all 64 rows used
+    (1, 256, 48, 80, 63),      # P4-like: 15 full tiles
+    (5, 256, 16, 16, 7),       # exactly one tile per map, few channels
+]
+
+
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("shape", WT_SHAPES)
+def test_tc_conv_weights_as_a_vs_fp64(shape, relu):
+    """k_conv3x3_wt (stacked [w_hi; w_lo] as the A operand, 256 pixels as N) against an fp64 convolution and
+    against the pixels-as-M kernel on the same inputs."""
+    NB, Cin, H, W, Cout = shape
+    g = torch.Generator().manual_seed(40 + Cout)
+    x = torch.randn((NB, Cin, H, W), generator=g) * 2.0
+    w = torch.randn((Cout, Cin, 3, 3), generator=g) * (2.0 / (9 * Cin)) ** 0.5
+    b = torch.randn((Cout,), generator=g) * 0.1
+    ref = G.conv_ref64(x, w, b, relu)
+    try:
+        ops.set_conv_wt(1)
+        got = G.tc_conv_raw(x, w, b, relu, cout_pad=64)
+        ops.set_conv_wt(0)
+        other = G.tc_conv_raw(x, w, b, relu, cout_pad=64)
+    finally:
+        ops.set_conv_wt(1)
+    assert not torch.isnan(got).any()          # the output buffer is NaN-filled: every valid element was written
+    err, err_other = G.rel_err(got, ref), G.rel_err(other, ref)
+    print("weights-as-A %s relu=%s: rel err vs fp64 %.3e (pixels-as-M: %.3e)" % (shape, relu, err, err_other))
+    assert err < 1e-5 and err_other < 1e-5
+    assert G.rel_err(got, other.double()) < 4e-6
+
+
 def test_tc_conv_chunked_accumulation_is_more_accurate():
     """tcgen05 accumulates with truncation; summing one tap per TMEM chain and adding the nine partial
     sums in fp32 RN (the default) must beat the single 2304-long chain and stay within 3e-6."""
