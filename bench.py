@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--halo", type=int, default=-1, help="1/0: row-halo activation staging on / one TMA box per tap")
     ap.add_argument("--chunk-taps", type=int, default=0, help="taps per accumulation chunk (1, 3, 9)")
     ap.add_argument("--chunk-kblocks", type=int, default=0, help="K-blocks per accumulation chunk (overrides --chunk-taps)")
+    ap.add_argument("--trunc-comp", type=float, default=-1.0, help="truncation compensation, ulps per MMA accumulation")
     args = ap.parse_args()
 
     from pod_compare_b200 import distributed as D
@@ -228,6 +229,8 @@ def main():
         ops.set_conv_chunk_taps(args.chunk_taps)
     if args.chunk_kblocks:
         ops.set_conv_chunk_kblocks(args.chunk_kblocks)
+    if args.trunc_comp >= 0:
+        ops.set_conv_trunc_comp(args.trunc_comp)
 
     cfg = build_cfg(args.n_mc, args.workload)
     pred = build_predictor(cfg)

@@ -142,9 +142,12 @@ int pod_conv3x3_tc_set_kblock(int bk);
  * the epilogue warps: 1 (default, most accurate), 3 or 9 (single chain; tcgen05 accumulates with
  * truncation, which drifts ~2e-5 relative over the 2304-long reduction). */
 int pod_conv3x3_tc_set_chunk_taps(int taps);
-/* Finer control: K-blocks per accumulation chunk (default 6 = 384 channels = 1.5 taps; 0 = use the taps
+/* Finer control: K-blocks per accumulation chunk (default 12 = 768 channels = 3 taps; 0 = use the taps
  * setting); ignored for a convolution whose K-block count it does not divide. */
 int pod_conv3x3_tc_set_chunk_kblocks(int kb);
+/* Compensation of the tensor core's accumulate-with-truncation: expected loss per MMA accumulation in fp32 ulps
+ * of the running sum (default 0.27, measured; 0 = off).  The epilogue scale is multiplied by 1 + ulps * (MMAs per TMEM chain) * 2^-24. */
+int pod_conv3x3_tc_set_trunc_comp(float ulps_per_mma);
 /* Weights-as-A kernel for RAW convolutions of <= 64 output channels (default on): the weight tile with its hi and
  * lo halves stacked along M is the A operand and 256 pixels are the N operand, two full-size MMAs per K-step.
  * Taken only when w_lo == w_hi + 64 rows (pod_pack_conv_weight into one buffer) and Cout_pad == 64. */

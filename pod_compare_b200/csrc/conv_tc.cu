@@ -1281,18 +1281,34 @@ static int dispatch_bn(const Params& P, cudaStream_t st) {
 
 }  // namespace tc
 
+static float g_tc_trunc_comp = 0.27f; // expected truncation loss per MMA accumulation, in fp32 ulps of the running sum (see
+                                      // pod_conv3x3_tc_set_trunc_comp); measured 0.27 (profiles/r1e_trunc_comp_*.txt); 0 = off
 static int g_tc_wt = 1;       // 1: output convolutions of <= 64 channels run weights-as-A (k_conv3x3_wt)
 static int g_tc_halo = 0;     // 1: row-halo staging (K-block 64 only): one 10-row activation box serves three taps.
                               // Off by default: measured equal on the narrow convs and ~1 % slower on the tower
 static int g_tc_bk = 64;      // K-block (channels per pipeline stage): 64 -> SWIZZLE_128B (default), 32 -> SWIZZLE_64B
 static int g_tc_taps = 1;     // taps per accumulation chunk (1, 3 or 9)
-static int g_tc_chunk_kb = 6; // if > 0: K-blocks per accumulation chunk (must divide 9*Cin/K-block); overrides taps.
-                              // default 6 x 64 channels = 1.5 taps: 6 TMEM drains per tile (measured trade-off in DESIGN.md)
+static int g_tc_chunk_kb = 12; // if > 0: K-blocks per accumulation chunk (must divide 9*Cin/K-block); overrides taps.
+                               // default 12 x 64 channels = 3 taps: 3 TMEM drains per tile; with the truncation compensation
+                               // this is more accurate than 6-K-block chunks without it and 10 % faster
 
 extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_chunk_kblocks(int kb) {
   POD_REQUIRE(kb >= 0, "pod_conv3x3_tc_set_chunk_kblocks: must be >= 0");
   g_tc_chunk_kb = kb;
   return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_trunc_comp(float ulps_per_mma) {
+  POD_REQUIRE(ulps_per_mma >= 0.f && ulps_per_mma < 4.f, "pod_conv3x3_tc_set_trunc_comp: 0 <= ulps < 4");
+  g_tc_trunc_comp = ulps_per_mma;
+  return 0;
+}
+
+// tcgen05 adds each MMA into the fp32 TMEM accumulator with truncation toward zero: a chain of n accumulations
+// comes out smaller by ~c*n*2^-24 relative (c measured, profiles/).  The factor is folded into the epilogue scale.
+static inline float trunc_comp_factor(int kb_per_chunk, int bk, int mmas_per_kstep) {
+  const double n = (double)kb_per_chunk * (bk / 16) * mmas_per_kstep;
+  return (float)(1.0 + (double)g_tc_trunc_comp * n * 5.9604644775390625e-08);
 }
 
 extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_wt(int on) {
@@ -1365,7 +1381,7 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
     P.relu = a->relu;
     P.kb_per_chunk = g_tc_taps * (a->Cin / 64);
     if (g_tc_chunk_kb > 0 && (9 * (a->Cin / 64)) % g_tc_chunk_kb == 0) P.kb_per_chunk = g_tc_chunk_kb;
-    P.acc_scale = 1.0f / (a->in_scale * a->w_scale);
+    P.acc_scale = 1.0f / (a->in_scale * a->w_scale) * trunc_comp_factor(P.kb_per_chunk, 64, 2);
     P.bias = a->bias;
     P.out_f32 = a->out_f32;
     P.out_map_stride = a->out_map_stride; P.out_pixel_stride = a->out_pixel_stride;
@@ -1400,7 +1416,7 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   P.kb_per_chunk = g_tc_taps * (a->Cin / BK);
   if (g_tc_chunk_kb > 0 && (9 * (a->Cin / BK)) % g_tc_chunk_kb == 0) P.kb_per_chunk = g_tc_chunk_kb;
   P.dbg_skip_ld = getenv("POD_TC_DEBUG_SKIP_LD") ? 1 : 0;
-  P.acc_scale = 1.0f / (a->in_scale * a->w_scale);
+  P.acc_scale = 1.0f / (a->in_scale * a->w_scale) * trunc_comp_factor(P.kb_per_chunk, BK, a->Cout_pad <= 128 ? 2 : 3);
   P.out_scale = a->out_scale;
   P.bias = a->bias;
   P.out_hi = (__half*)a->out_hi; P.out_lo = (__half*)a->out_lo; P.out_f32 = a->out_f32;

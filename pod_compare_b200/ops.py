@@ -195,6 +195,10 @@ def set_conv_pair(on):
     check(_cabi.load_library().pod_conv3x3_tc_set_pair(int(bool(on))), "pod_conv3x3_tc_set_pair")
 
 
+def set_conv_trunc_comp(ulps_per_mma):
+    check(_cabi.load_library().pod_conv3x3_tc_set_trunc_comp(float(ulps_per_mma)), "pod_conv3x3_tc_set_trunc_comp")
+
+
 def set_conv_wt(on):
     check(_cabi.load_library().pod_conv3x3_tc_set_wt(int(bool(on))), "pod_conv3x3_tc_set_wt")
 

@@ -195,10 +195,34 @@ def test_tc_conv_chunked_accumulation_is_more_accurate():
             err[taps] = G.rel_err(G.tc_conv_raw(x, w, b, False), ref)
     finally:
         ops.set_conv_chunk_taps(1)
-        ops.set_conv_chunk_kblocks(6)
+        ops.set_conv_chunk_kblocks(12)
     print("conv rel err vs fp64: single chain %.3e, per-tap chunks %.3e" % (err[9], err[1]))
     assert err[1] < 3e-6
     assert err[1] < err[9]
+
+
+def test_truncation_compensation_removes_the_accumulation_bias():
+    """tcgen05 adds every MMA into the fp32 accumulator with truncation toward zero, so a TMEM chain of n
+    accumulations comes out ~0.27*n*2^-24 too small (measured: profiles/r1e_trunc_comp_robustness.txt).  The
+    default epilogue scale compensates the expected loss: the signed bias against an fp64 convolution must vanish
+    and the rms error must drop, for signed and for ReLU inputs."""
+    g = torch.Generator().manual_seed(21)
+    w = torch.randn((256, 256, 3, 3), generator=g) * (2.0 / 2304) ** 0.5
+    b = torch.zeros(256)
+    for x in (torch.relu(torch.randn((1, 256, 24, 40), generator=g)) * 1.25, torch.randn((1, 256, 24, 40), generator=g)):
+        ref = G.conv_ref64(x, w, b, False)
+        out = {}
+        try:
+            for comp in (0.0, 0.27):
+                ops.set_conv_trunc_comp(comp)
+                d = G.tc_conv_raw(x, w, b, False).double() - ref
+                out[comp] = (float((d * ref.sign()).mean() / ref.abs().mean()), float(d.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()))
+        finally:
+            ops.set_conv_trunc_comp(0.27)
+        print("bias / rms vs fp64: uncompensated %+.2e / %.2e, compensated %+.2e / %.2e" % (out[0.0] + out[0.27]))
+        assert out[0.0][0] < -1.5e-6                  # the raw chain (12 K-blocks = 144 accumulations) is biased low
+        assert abs(out[0.27][0]) < 3e-7               # compensated: no bias left
+        assert out[0.27][1] < 0.7 * out[0.0][1] and out[0.27][1] < 2e-6
 
 
 @pytest.mark.parametrize("halo", [1, 0])

@@ -1,5 +1,5 @@
 """End-to-end accuracy at the benchmark geometry (1280x720, reg_cls_var_dropout, MC-dropout N small
-enough for the CPU oracle) for the three accumulation-chunk settings of the tcgen05 convolution.
+enough for the CPU oracle) for accumulation-chunk / truncation-compensation settings of the tcgen05 convolution.
     python tools/e2e_accuracy.py [N]        (needs a B200; the oracle runs on the host cores)"""
 import os
 import sys
@@ -31,12 +31,10 @@ pred = build_predictor(cfg)
 pred.skip_unread_outputs = False      # the raw outputs of every sample are inspected below
 pred.load_weight_sets(sd)
 ids_ref = {int(a): i for i, a in enumerate(ref_cand.anchor_ids)}
-for taps in (1, -6, -9, 3, 9):
-    if taps < 0:
-        ops.set_conv_chunk_kblocks(-taps)          # K-blocks of 64 channels per chunk (1.5 / 2.25 taps)
-    else:
-        ops.set_conv_chunk_kblocks(0)
-        ops.set_conv_chunk_taps(taps)
+for kb, comp in ((6, 0.0), (6, 0.27), (9, 0.27), (12, 0.0), (12, 0.27), (18, 0.27), (36, 0.0), (36, 0.27)):
+    ops.set_conv_chunk_kblocks(kb)                 # K-blocks of 64 channels per TMEM chain (4 = one tap, 36 = single chain)
+    ops.set_conv_trunc_comp(comp)                  # truncation compensation, ulps per MMA accumulation
+    taps = -kb
     res, raw, cand, det = pred.infer_from_features(feats, (H, W), (H, W), image0=0, seed=7, return_raw=True)
     torch.cuda.synchronize()
     dl = max(float((raw["logits"][0, s].cpu() - torch.cat([o[0] for o in outs[s]["box_cls"]], 0)).abs().max()) for s in range(N))
@@ -49,9 +47,9 @@ for taps in (1, -6, -9, 3, 9):
     bx = cand["boxes"][0, :M].cpu().numpy()[ig]; bxr = ref_cand.boxes.numpy()[ir]
     cv = cand["cov"][0, :M].cpu().numpy()[ig].astype(np.float64); cvr = ref_cand.cov.numpy()[ir].astype(np.float64)
     scale = np.abs(cvr).reshape(len(ir), -1).max(1).reshape(-1, 1, 1)
-    print("chunk = %s: max|dlogit| %.2e  max|ddelta| %.2e | candidates %d/%d common | score rel %.2e | box abs %.2e px | "
+    print("chunk = %s, comp %.2f: max|dlogit| %.2e  max|ddelta| %.2e | candidates %d/%d common | score rel %.2e | box abs %.2e px | "
           "cov rel(matrix max) %.2e | detections %d vs %d"
-          % (("%d tap(s)" % taps) if taps > 0 else ("%d K-blocks" % -taps), dl, dd, len(common), ref_cand.boxes.shape[0], float(np.abs(sc / scr - 1).max()), float(np.abs(bx - bxr).max()),
+          % (("%d tap(s)" % taps) if taps > 0 else ("%d K-blocks" % -taps), comp, dl, dd, len(common), ref_cand.boxes.shape[0], float(np.abs(sc / scr - 1).max()), float(np.abs(bx - bxr).max()),
              float((np.abs(cv - cvr) / scale).max()), len(res[0]), ref_final.boxes.shape[0]))
-ops.set_conv_chunk_taps(1)
-ops.set_conv_chunk_kblocks(6)
+ops.set_conv_trunc_comp(0.27)
+ops.set_conv_chunk_kblocks(12)
