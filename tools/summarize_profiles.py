@@ -66,11 +66,17 @@ def launches(tag):
     for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
         lines.append("%-100s %6d %11.3f %6.1f%%" % (k[:100], n, ms, 100 * ms / tot))
     for k, (n, ms) in agg.items():
-        if "k_conv3x3_tc" in k:
+        if "k_conv3x3_" in k:
             conv += ms
     lines += ["", "all tcgen05 conv launches: %.1f%% of kernel time" % (100 * conv / tot)]
     shutil.copy(path, os.path.join(PR, "%s_launches_batch4.csv" % tag))
     return lines
+
+
+def bench_workloads():
+    sys.path.insert(0, ROOT)
+    import bench
+    return bench.WORKLOADS
 
 
 def main():
@@ -99,10 +105,26 @@ def main():
                "dram_bytes_read": rd, "dram_bytes_write": wr, "algorithmic_bytes": alg, "maps": live_maps, "H": 96, "W": 160},
               open(os.path.join(PR, "conv_traffic.json"), "w"), indent=1)
     lines, _ = ncu_summary(tag, "out", [
-        "# %s: ncu --set full --clock-control none -k regex:^k_conv3x3_tc$ -c 3  (bench.py --batch 2 --chunk 2)" % tag,
-        "# kernels: the narrow output convolutions at P3 (cls_score 63->64, cls_var 63->64, bbox_pred 36->48), single CTA,",
-        "# N-stacked hi|lo weights (2 MMAs per K-step)"])
+        "# %s: ncu --set full --clock-control none -k regex:^k_conv3x3_wt$ -c 3  (bench.py --batch 2 --chunk 2)" % tag,
+        "# kernels: the output convolutions at P3 (cls_score 63, cls_var 63, bbox_pred 36 channels, all padded to 64 rows), single CTA,",
+        "# weights-as-A: stacked [w_hi; w_lo] as the M=128 operand, 16x16 pixels as N=256, 2 MMAs per K-step"])
     open(os.path.join(PR, "%s_out_conv_ncu_full.txt" % tag), "w").write("\n".join(lines) + "\n")
+    side = os.path.join(GO, "%s_side_workloads.jsonl" % tag)
+    if os.path.exists(side):
+        out = ["# %s side workloads on ONE B200, batch 32 per step (python bench.py --workload <w> --no-cpu-baseline); not the headline metric" % tag,
+               "%-14s %9s %10s %9s %11s %9s %7s" % ("workload", "images/s", "e2e img/s", "mma_frac", "conv share", "launches", "SM MHz")]
+        for ln in open(side):
+            ln = ln.strip()
+            if not ln.startswith("{"):
+                continue
+            j = json.loads(ln)
+            r = j.get("roofline") or {}
+            wl = j["config"]["workload"]
+            name = [k for k, v in bench_workloads().items() if wl.startswith(v[0])]
+            out.append("%-14s %9.1f %10.1f %9.3f %11.3f %9d %7s   # %s" % (name[0] if name else "?", j["value"], j["e2e"]["value"],
+                       r.get("mma_frac", float("nan")), r.get("conv_share_of_step", float("nan")), j["gpu_launches"],
+                       j["clocks"]["sm_mhz"], wl))
+        open(os.path.join(PR, "%s_side_workloads.txt" % tag), "w").write("\n".join(out) + "\n")
     print("value", bj["value"], "e2e", bj["e2e"]["value"], "roofline", bj["roofline"]["frac"], bj["roofline"]["mma_frac"])
 
 
