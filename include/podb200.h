@@ -152,10 +152,11 @@ int pod_conv3x3_tc_set_trunc_comp(float ulps_per_mma);
  * lo halves stacked along M is the A operand and 256 pixels are the N operand, two full-size MMAs per K-step.
  * Taken only when w_lo == w_hi + 64 rows (pod_pack_conv_weight into one buffer) and Cout_pad == 64. */
 int pod_conv3x3_tc_set_wt(int on);
-/* Row-halo activation staging (default off, K-block 64 only): one 10-row x 16-column TMA box per column shift
- * serves the three row-shifted taps through descriptor offsets, cutting activation bytes into the SM 2.4x.
- * Process-wide tuning knob; the K order of the accumulation differs (results agree to fp32 round-off). */
-int pod_conv3x3_tc_set_halo(int on);
+/* Row-halo activation staging (K-block 64 only): one TMA box two rows taller than the pixel tile per column shift
+ * serves the three row-shifted taps through descriptor offsets, cutting activation bytes into the SM ~2.5x.
+ * mode bit 0: pixels-as-M kernels (default off), bit 1: weights-as-A kernel (default on).  Process-wide tuning
+ * knob; the K order of the accumulation differs (results agree to fp32 round-off). */
+int pod_conv3x3_tc_set_halo(int mode);
 /* 256-output-channel convolutions on CTA pairs (tcgen05 cta_group::2, default on) or on single CTAs. */
 int pod_conv3x3_tc_set_pair(int on);
 /* Device-side error word of the last tcgen05 launch on this thread (0 = ok; set when a bounded

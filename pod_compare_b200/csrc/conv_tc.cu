@@ -1047,17 +1047,25 @@ static int launch2(const Params& P, cudaStream_t st) {
 constexpr int WT_TILE = 16;                        // 16 x 16 pixel tile
 constexpr int WT_X_STAGE = 256 * 128;              // one of (hi, lo): 256 pixels x 64 channels
 constexpr int WT_W_STAGE = 128 * 128;              // [w_hi (64 rows); w_lo (64 rows)] x 64 channels
+constexpr int WT_XH_STAGE = (WT_TILE + 2) * WT_TILE * 128;   // row-halo staging: 18 rows x 16 pixels serve three taps
 constexpr int WT_X_STAGES = 4;
 constexpr int WT_W_STAGES = 3;
 constexpr int WT_XCHG = 2 * 64 * 64 * 4;           // lane-half exchange: 2 column halves x 64 columns x 64 rows fp32
-constexpr int WT_SMEM = 1024 + WT_X_STAGES * WT_X_STAGE + WT_W_STAGES * WT_W_STAGE + WT_XCHG;
+constexpr int WT_SMEM = 1024 + WT_X_STAGES * WT_XH_STAGE + WT_W_STAGES * WT_W_STAGE + WT_XCHG;
 static_assert(WT_SMEM <= 227 * 1024, "weights-as-A kernel exceeds shared memory");
+static_assert(WT_XH_STAGE % 1024 == 0 && WT_X_STAGES % 2 == 0, "pixel stages keep swizzle-atom alignment, hi/lo pairs");
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// HALO: one 18-row x 16-column box per column shift dx (and per hi / lo part) serves the three row shifts dy through
+// descriptor offsets of dy * 2048 B (as in the pixels-as-M HALO kernels): the pixel bytes into the SM drop 2.7x, which
+// matters here because this kernel pulls 65 B/clk/SM through L2 (ncu: lts 61 %, a quarter of the issue time waiting
+// for operands).  Pixel stages then come in (hi, lo) pairs that are held for three weight stages.
+template <bool HALO>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_wt(const __grid_constant__ Params P) {
+  constexpr int XS = HALO ? WT_XH_STAGE : WT_X_STAGE;          // bytes of one pixel stage
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   constexpr int COLS = 128, NG = 8, EPI_THREADS = 256;
   extern __shared__ uint8_t smem_dyn[];
@@ -1072,7 +1080,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_wt(const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   uint8_t* smem = smem_dyn + (smem_base - smem_u32(smem_dyn));
-  constexpr uint32_t W_OFF = WT_X_STAGES * WT_X_STAGE;
+  constexpr uint32_t W_OFF = WT_X_STAGES * WT_XH_STAGE;
   constexpr uint32_t XCHG_OFF = W_OFF + WT_W_STAGES * WT_W_STAGE;
 
   if (warp == 0 && lane == 0) {
@@ -1116,6 +1124,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_wt(const __grid_cons
       for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
         const int n = physical_map(P, tile / tiles_per_map), r = tile % tiles_per_map;
         const int y0 = (r / P.tiles_x) * WT_TILE, x0 = (r % P.tiles_x) * WT_TILE;
+        if constexpr (HALO) {
+          for (int cb = 0; cb < kb_per_tap && ok; ++cb) {
+            for (int dx = 0; dx < 3 && ok; ++dx) {
+              for (int part = 0; part < 2; ++part) {
+                if (!mbar_wait(&xempty_bar[xs], xphase ^ 1u, 22)) { ok = false; break; }
+                mbar_arrive_expect_tx(&xfull_bar[xs], (uint32_t)XS);
+                tma_load_4d(part == 0 ? &P.tm_a_hi : &P.tm_a_lo, &xfull_bar[xs], smem + (size_t)xs * XS, cb * 64, x0 + dx - 1, y0 - 1, n);
+                if (++xs == WT_X_STAGES) { xs = 0; xphase ^= 1u; }
+              }
+              for (int dy = 0; dy < 3 && ok; ++dy) {
+                if (!mbar_wait(&wempty_bar[ws], wphase ^ 1u, 21)) { ok = false; break; }
+                mbar_arrive_expect_tx(&wfull_bar[ws], (uint32_t)WT_W_STAGE);
+                tma_load_2d(&P.tm_b_hi, &wfull_bar[ws], smem + W_OFF + (size_t)ws * WT_W_STAGE, (dy * 3 + dx) * P.Cin + cb * 64, 0);
+                if (++ws == WT_W_STAGES) { ws = 0; wphase ^= 1u; }
+              }
+            }
+          }
+        } else
         for (int tap = 0; tap < 9 && ok; ++tap) {
           const int yy = y0 + tap / 3 - 1, xx = x0 + tap % 3 - 1;
           for (int cb = 0; cb < kb_per_tap && ok; ++cb) {
@@ -1125,8 +1151,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_wt(const __grid_cons
             if (++ws == WT_W_STAGES) { ws = 0; wphase ^= 1u; }
             for (int part = 0; part < 2; ++part) {
               if (!mbar_wait(&xempty_bar[xs], xphase ^ 1u, 22)) { ok = false; break; }
-              mbar_arrive_expect_tx(&xfull_bar[xs], (uint32_t)WT_X_STAGE);
-              tma_load_4d(part == 0 ? &P.tm_a_hi : &P.tm_a_lo, &xfull_bar[xs], smem + (size_t)xs * WT_X_STAGE, cb * 64, xx, yy, n);
+              mbar_arrive_expect_tx(&xfull_bar[xs], (uint32_t)XS);
+              tma_load_4d(part == 0 ? &P.tm_a_hi : &P.tm_a_lo, &xfull_bar[xs], smem + (size_t)xs * XS, cb * 64, xx, yy, n);
               if (++xs == WT_X_STAGES) { xs = 0; xphase ^= 1u; }
             }
           }
@@ -1138,6 +1164,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_wt(const __grid_cons
       uint32_t xs = 0, xphase = 0, ws = 0, wphase = 0, acc = 0, acc_phase = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
+        int dy = 0;                                       // HALO: unit order (K-block, dx, dy), dy fastest
         for (int c = 0; c < n_chunks && ok; ++c) {
           if (!mbar_wait_all(&tempty_bar[acc], acc_phase ^ 1u, 23)) { ok = false; break; }
           tcgen05_fence_after();
@@ -1145,17 +1172,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_wt(const __grid_cons
           for (int j = 0; j < kb_per_chunk && ok; ++j) {
             if (!mbar_wait_all(&wfull_bar[ws], wphase, 24)) { ok = false; break; }
             const uint64_t w0 = make_smem_desc<128>(smem_base + W_OFF + ws * WT_W_STAGE);
-            for (int part = 0; part < 2; ++part) {
-              if (!mbar_wait_all(&xfull_bar[xs], xphase, 25)) { ok = false; break; }
-              tcgen05_fence_after();
-              const uint64_t x0d = make_smem_desc<128>(smem_base + xs * WT_X_STAGE);
-#pragma unroll
-              for (int k = 0; k < 64 / UMMA_K; ++k) {
-                const uint64_t koff = (uint64_t)(k * UMMA_K * 2) >> 4;
-                umma_f16(d_tmem, w0 + koff, x0d + koff, IDESC, (j | part | k) != 0 ? 1u : 0u, leader);
+            if constexpr (HALO) {
+              if (dy == 0) {                              // a fresh (hi, lo) pair of pixel stages: xs, xs + 1
+                if (!mbar_wait_all(&xfull_bar[xs], xphase, 25)) { ok = false; break; }
+                if (!mbar_wait_all(&xfull_bar[xs + 1], xphase, 25)) { ok = false; break; }
               }
-              umma_commit(&xempty_bar[xs], leader);
-              if (++xs == WT_X_STAGES) { xs = 0; xphase ^= 1u; }
+              tcgen05_fence_after();
+#pragma unroll
+              for (int part = 0; part < 2; ++part) {
+                const uint64_t x0d = make_smem_desc<128>(smem_base + (xs + part) * XS + dy * (WT_TILE * 128));
+#pragma unroll
+                for (int k = 0; k < 64 / UMMA_K; ++k) {
+                  const uint64_t koff = (uint64_t)(k * UMMA_K * 2) >> 4;
+                  umma_f16(d_tmem, w0 + koff, x0d + koff, IDESC, (j | part | k) != 0 ? 1u : 0u, leader);
+                }
+              }
+              if (++dy == 3) {                            // third row shift done: both pixel stages are free
+                dy = 0;
+                umma_commit(&xempty_bar[xs], leader);
+                umma_commit(&xempty_bar[xs + 1], leader);
+                xs += 2;
+                if (xs == WT_X_STAGES) { xs = 0; xphase ^= 1u; }
+              }
+            } else {
+              for (int part = 0; part < 2; ++part) {
+                if (!mbar_wait_all(&xfull_bar[xs], xphase, 25)) { ok = false; break; }
+                tcgen05_fence_after();
+                const uint64_t x0d = make_smem_desc<128>(smem_base + xs * XS);
+#pragma unroll
+                for (int k = 0; k < 64 / UMMA_K; ++k) {
+                  const uint64_t koff = (uint64_t)(k * UMMA_K * 2) >> 4;
+                  umma_f16(d_tmem, w0 + koff, x0d + koff, IDESC, (j | part | k) != 0 ? 1u : 0u, leader);
+                }
+                umma_commit(&xempty_bar[xs], leader);
+                if (++xs == WT_X_STAGES) { xs = 0; xphase ^= 1u; }
+              }
             }
             umma_commit(&wempty_bar[ws], leader);
             if (++ws == WT_W_STAGES) { ws = 0; wphase ^= 1u; }
@@ -1249,14 +1300,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_wt(const __grid_cons
   }
 }
 
+template <bool HALO>
 static int launch_wt(const Params& P, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    POD_CUDA(cudaFuncSetAttribute(k_conv3x3_wt, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+    POD_CUDA(cudaFuncSetAttribute(k_conv3x3_wt<HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
     configured = true;
   }
   const int grid = P.num_tiles < pod_num_sms() ? P.num_tiles : pod_num_sms();
-  k_conv3x3_wt<<<grid, NUM_THREADS, WT_SMEM, st>>>(P);
+  k_conv3x3_wt<HALO><<<grid, NUM_THREADS, WT_SMEM, st>>>(P);
   POD_LAUNCH_CHECK();
   return 0;
 }
@@ -1284,8 +1336,9 @@ static int dispatch_bn(const Params& P, cudaStream_t st) {
 static float g_tc_trunc_comp = 0.27f; // expected truncation loss per MMA accumulation, in fp32 ulps of the running sum (see
                                       // pod_conv3x3_tc_set_trunc_comp); measured 0.27 (profiles/r1e_trunc_comp_*.txt); 0 = off
 static int g_tc_wt = 1;       // 1: output convolutions of <= 64 channels run weights-as-A (k_conv3x3_wt)
-static int g_tc_halo = 0;     // 1: row-halo staging (K-block 64 only): one 10-row activation box serves three taps.
-                              // Off by default: measured equal on the narrow convs and ~1 % slower on the tower
+static int g_tc_halo = 2;     // row-halo staging (K-block 64 only), bit 0: pixels-as-M kernels (one 10-row box serves three taps;
+                              // measured equal on the narrow convs and ~1 % slower on the tower: off), bit 1: weights-as-A
+                              // kernel (18-row boxes; +0.8 % on the step: on).  DESIGN.md 3.1a
 static int g_tc_bk = 64;      // K-block (channels per pipeline stage): 64 -> SWIZZLE_128B (default), 32 -> SWIZZLE_64B
 static int g_tc_taps = 1;     // taps per accumulation chunk (1, 3 or 9)
 static int g_tc_chunk_kb = 12; // if > 0: K-blocks per accumulation chunk (must divide 9*Cin/K-block); overrides taps.
@@ -1316,8 +1369,9 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_wt(int 
   return 0;
 }
 
-extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_halo(int on) {
-  g_tc_halo = on ? 1 : 0;
+extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_halo(int mode) {
+  POD_REQUIRE(mode >= 0 && mode <= 3, "pod_conv3x3_tc_set_halo: bit 0 = pixels-as-M kernels, bit 1 = weights-as-A kernel");
+  g_tc_halo = mode;
   return 0;
 }
 
@@ -1358,8 +1412,10 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   if (wt) {
     POD_REQUIRE(a->out_f32 && a->out_pixel_stride >= a->Cout, "pod_conv3x3_tc: raw mode needs out_f32 / pixel stride >= Cout");
     int rc;
-    if ((rc = encode_act(&P.tm_a_hi, a->in_hi, a->Cin, a->W, a->H, a->NB, a->in_map_stride, 64, WT_TILE, WT_TILE))) return rc;
-    if ((rc = encode_act(&P.tm_a_lo, a->in_lo, a->Cin, a->W, a->H, a->NB, a->in_map_stride, 64, WT_TILE, WT_TILE))) return rc;
+    const bool wt_halo = (g_tc_halo & 2) != 0;
+    const int wt_rows = wt_halo ? WT_TILE + 2 : WT_TILE;
+    if ((rc = encode_act(&P.tm_a_hi, a->in_hi, a->Cin, a->W, a->H, a->NB, a->in_map_stride, 64, wt_rows, WT_TILE))) return rc;
+    if ((rc = encode_act(&P.tm_a_lo, a->in_lo, a->Cin, a->W, a->H, a->NB, a->in_map_stride, 64, wt_rows, WT_TILE))) return rc;
     if ((rc = encode_wt(&P.tm_b_hi, a->w_hi, 9 * a->Cin, 128, 64, 128))) return rc;
     P.tm_b_lo = P.tm_b_hi;
     P.NB = a->NB; P.H = a->H; P.W = a->W; P.Cin = a->Cin;
@@ -1385,9 +1441,9 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
     P.bias = a->bias;
     P.out_f32 = a->out_f32;
     P.out_map_stride = a->out_map_stride; P.out_pixel_stride = a->out_pixel_stride;
-    return launch_wt(P, (cudaStream_t)stream);
+    return wt_halo ? launch_wt<true>(P, (cudaStream_t)stream) : launch_wt<false>(P, (cudaStream_t)stream);
   }
-  const bool halo = g_tc_halo && BK == 64;
+  const bool halo = (g_tc_halo & 1) && BK == 64;
   const int box_rows = halo ? HALO_ROWS : TILE_H;
   int rc;
   if ((rc = encode_act(&P.tm_a_hi, a->in_hi, a->Cin, a->W, a->H, a->NB, a->in_map_stride, BK, box_rows))) return rc;

@@ -203,8 +203,9 @@ def set_conv_wt(on):
     check(_cabi.load_library().pod_conv3x3_tc_set_wt(int(bool(on))), "pod_conv3x3_tc_set_wt")
 
 
-def set_conv_halo(on):
-    check(_cabi.load_library().pod_conv3x3_tc_set_halo(int(bool(on))), "pod_conv3x3_tc_set_halo")
+def set_conv_halo(mode):
+    """Row-halo operand staging: bit 0 = pixels-as-M kernels, bit 1 = weights-as-A kernel."""
+    check(_cabi.load_library().pod_conv3x3_tc_set_halo(int(mode)), "pod_conv3x3_tc_set_halo")
 
 
 def set_conv_chunk_kblocks(kb):

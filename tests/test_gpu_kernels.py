@@ -124,7 +124,7 @@ def test_tc_conv_raw_vs_fp64(shape, staging, pair):
         pytest.skip("single-CTA / paired choice only exists for 256 output channels")
     kblock = 32 if staging == "tap32" else 64
     ops.set_conv_kblock(kblock)
-    ops.set_conv_halo(staging == "halo64")
+    ops.set_conv_halo(1 if staging == "halo64" else 0)
     ops.set_conv_pair(pair)
     try:
         g = torch.Generator().manual_seed(4)
@@ -140,9 +140,11 @@ def test_tc_conv_raw_vs_fp64(shape, staging, pair):
         assert err < 1e-5
     finally:
         ops.set_conv_kblock(64)
-        ops.set_conv_halo(0)
+        ops.set_conv_halo(DEFAULT_HALO)
         ops.set_conv_pair(1)
 
+
+DEFAULT_HALO = 2     # library default of pod_conv3x3_tc_set_halo (bit 1 = weights-as-A kernel)
 
 WT_SHAPES = [  # (NB, Cin, H, W, Cout): output convolutions of <= 64 channels run weights-as-A (16x16 pixel tiles)
     (2, 256, 6, 10, 63),       # P7-like: one partial tile
@@ -154,9 +156,10 @@ WT_SHAPES = [  # (NB, Cin, H, W, Cout): output convolutions of <= 64 channels ru
 ]
 
 
+@pytest.mark.parametrize("halo", [2, 0])
 @pytest.mark.parametrize("relu", [False, True])
 @pytest.mark.parametrize("shape", WT_SHAPES)
-def test_tc_conv_weights_as_a_vs_fp64(shape, relu):
+def test_tc_conv_weights_as_a_vs_fp64(shape, relu, halo):
     """k_conv3x3_wt (stacked [w_hi; w_lo] as the A operand, 256 pixels as N) against an fp64 convolution and
     against the pixels-as-M kernel on the same inputs."""
     NB, Cin, H, W, Cout = shape
@@ -167,11 +170,14 @@ def test_tc_conv_weights_as_a_vs_fp64(shape, relu):
     ref = G.conv_ref64(x, w, b, relu)
     try:
         ops.set_conv_wt(1)
+        ops.set_conv_halo(halo)                 # 2: 18-row pixel boxes shared by three taps; 0: one box per tap
         got = G.tc_conv_raw(x, w, b, relu, cout_pad=64)
         ops.set_conv_wt(0)
+        ops.set_conv_halo(0)
         other = G.tc_conv_raw(x, w, b, relu, cout_pad=64)
     finally:
         ops.set_conv_wt(1)
+        ops.set_conv_halo(DEFAULT_HALO)
     assert not torch.isnan(got).any()          # the output buffer is NaN-filled: every valid element was written
     err, err_other = G.rel_err(got, ref), G.rel_err(other, ref)
     print("weights-as-A %s relu=%s: rel err vs fp64 %.3e (pixels-as-M: %.3e)" % (shape, relu, err, err_other))
@@ -231,7 +237,7 @@ def test_tc_conv_hidden_dropout_and_strided_input(halo):
     try:
         _hidden_dropout_and_strided_input()
     finally:
-        ops.set_conv_halo(0)
+        ops.set_conv_halo(DEFAULT_HALO)
 
 
 def _hidden_dropout_and_strided_input():
