@@ -200,7 +200,7 @@ def main():
     ap.add_argument("--keep-unread", action="store_true",
                     help="also evaluate the last sample's class / variance tower passes, whose outputs the reference "
                          "computes but never reads (default: left out, results identical)")
-    ap.add_argument("--halo", type=int, default=-1, help="row-halo activation staging: bit 0 = pixels-as-M kernels, bit 1 = weights-as-A kernel (default 2)")
+    ap.add_argument("--halo", type=int, default=-1, help="row-halo activation staging: bit 0 = pixels-as-M kernels, bit 1 = weights-as-A kernel (default 3)")
     ap.add_argument("--chunk-taps", type=int, default=0, help="taps per accumulation chunk (1, 3, 9)")
     ap.add_argument("--chunk-kblocks", type=int, default=0, help="K-blocks per accumulation chunk (overrides --chunk-taps)")
     ap.add_argument("--trunc-comp", type=float, default=-1.0, help="truncation compensation, ulps per MMA accumulation")

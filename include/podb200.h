@@ -154,7 +154,7 @@ int pod_conv3x3_tc_set_trunc_comp(float ulps_per_mma);
 int pod_conv3x3_tc_set_wt(int on);
 /* Row-halo activation staging (K-block 64 only): one TMA box two rows taller than the pixel tile per column shift
  * serves the three row-shifted taps through descriptor offsets, cutting activation bytes into the SM ~2.5x.
- * mode bit 0: pixels-as-M kernels (default off), bit 1: weights-as-A kernel (default on).  Process-wide tuning
+ * mode bit 0: pixels-as-M kernels, bit 1: weights-as-A kernel (default 3 = both).  Process-wide tuning
  * knob; the K order of the accumulation differs (results agree to fp32 round-off). */
 int pod_conv3x3_tc_set_halo(int mode);
 /* 256-output-channel convolutions on CTA pairs (tcgen05 cta_group::2, default on) or on single CTAs. */

@@ -1336,9 +1336,9 @@ static int dispatch_bn(const Params& P, cudaStream_t st) {
 static float g_tc_trunc_comp = 0.27f; // expected truncation loss per MMA accumulation, in fp32 ulps of the running sum (see
                                       // pod_conv3x3_tc_set_trunc_comp); measured 0.27 (profiles/r1e_trunc_comp_*.txt); 0 = off
 static int g_tc_wt = 1;       // 1: output convolutions of <= 64 channels run weights-as-A (k_conv3x3_wt)
-static int g_tc_halo = 2;     // row-halo staging (K-block 64 only), bit 0: pixels-as-M kernels (one 10-row box serves three taps;
-                              // measured equal on the narrow convs and ~1 % slower on the tower: off), bit 1: weights-as-A
-                              // kernel (18-row boxes; +0.8 % on the step: on).  DESIGN.md 3.1a
+static int g_tc_halo = 3;     // row-halo staging (K-block 64 only), bit 0: pixels-as-M kernels (one 10-row box serves three taps),
+                              // bit 1: weights-as-A kernel (18-row boxes).  Both on: with 3 drains per tile the tower is
+                              // purely power-bound and the L2->SM bytes saved buy clock (+3 % on the step).  DESIGN.md 3.1a
 static int g_tc_bk = 64;      // K-block (channels per pipeline stage): 64 -> SWIZZLE_128B (default), 32 -> SWIZZLE_64B
 static int g_tc_taps = 1;     // taps per accumulation chunk (1, 3 or 9)
 static int g_tc_chunk_kb = 12; // if > 0: K-blocks per accumulation chunk (must divide 9*Cin/K-block); overrides taps.

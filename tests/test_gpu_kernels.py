@@ -144,7 +144,7 @@ def test_tc_conv_raw_vs_fp64(shape, staging, pair):
         ops.set_conv_pair(1)
 
 
-DEFAULT_HALO = 2     # library default of pod_conv3x3_tc_set_halo (bit 1 = weights-as-A kernel)
+DEFAULT_HALO = 3     # library default of pod_conv3x3_tc_set_halo (bit 1 = weights-as-A kernel)
 
 WT_SHAPES = [  # (NB, Cin, H, W, Cout): output convolutions of <= 64 channels run weights-as-A (16x16 pixel tiles)
     (2, 256, 6, 10, 63),       # P7-like: one partial tile
