@@ -80,6 +80,7 @@ class ProbabilisticPredictor:
         # (reference probabilistic_inference.py:216-267 loops over range(len-1)): the tower passes feeding
         # only those outputs are left out.  Results are unchanged; set False to evaluate them anyway.
         self.skip_unread_outputs = True
+        self._copy_stream = None          # host->device prefetch of the next chunk (infer_from_features chunk_images)
         self.rng_seed = int(self.cfg.SEED) if int(self.cfg.SEED) >= 0 else 0
         self.weight_sets = []
         self._engine = None
@@ -170,12 +171,20 @@ class ProbabilisticPredictor:
         return self.infer_from_features(feats, hw[0], out_hw[0], image0=image0)
 
     def infer_from_features(self, feats, image_hw, out_hw=None, image0=0, seed=None, return_raw=False,
-                            return_candidates=False):
+                            return_candidates=False, chunk_images=None):
         """feats: list over FPN levels of (B,256,Hl,Wl) fp32 tensors (host or device).
         image_hw: size of the network input (Instances.image_size before rescale,
-        inference_utils.py:39-41); out_hw: requested output resolution (:374-397)."""
+        inference_utils.py:39-41); out_hw: requested output resolution (:374-397).
+        chunk_images: evaluate the batch in chunks of at most this many images (bounds the activation memory:
+        2 x chunk x N x passes maps per level); host-resident features of chunk i+1 are uploaded on a copy stream
+        while chunk i computes.  Results are identical to one call per chunk (noise streams are keyed by image id)."""
         if self._engine is None:
             raise _cabi.PodError("no weights loaded: call load_weight_sets(state_dicts) first")
+        B = int(feats[0].shape[0])
+        if chunk_images is not None and 0 < int(chunk_images) < B:
+            if return_raw:
+                raise ValueError("return_raw is per chunk: call infer_from_features once per chunk")
+            return self._infer_chunked(feats, image_hw, out_hw, image0, seed, return_candidates, int(chunk_images))
         mode = self.inference_mode
         pi = self.cfg.PROBABILISTIC_INFERENCE
         post_nms = ((mode == 'mc_dropout_ensembles' and pi.ENSEMBLES_DROPOUT.BOX_MERGE_MODE != 'pre_nms') or
@@ -208,6 +217,47 @@ class ProbabilisticPredictor:
         if return_raw or return_candidates:
             return res, (raw if return_raw else None), cand, det
         return res
+
+    def _infer_chunked(self, feats, image_hw, out_hw, image0, seed, return_candidates, chunk):
+        B = int(feats[0].shape[0])
+        main = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        bounds = [(c0, min(B, c0 + chunk)) for c0 in range(0, B, chunk)]
+
+        def stage(c0, c1):
+            """Slice of the batch on the device + the event after which it may be read."""
+            if all(f.is_cuda for f in feats):
+                return [f[c0:c1] for f in feats], None
+            with torch.cuda.stream(self._copy_stream):
+                dev = [f[c0:c1].to(self.device, dtype=torch.float32, non_blocking=True) for f in feats]
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            for t in dev:
+                t.record_stream(main)              # allocated on the copy stream, consumed on the compute stream
+            return dev, ev
+
+        res, cands, dets = [], [], []
+        nxt = stage(*bounds[0])
+        for i, (c0, c1) in enumerate(bounds):
+            cur, ev = nxt
+            if i + 1 < len(bounds):
+                nxt = stage(*bounds[i + 1])        # issued before this chunk's kernels: overlaps with them
+            if ev is not None:
+                main.wait_event(ev)
+            out = self.infer_from_features(cur, image_hw, out_hw, image0=image0 + c0, seed=seed, return_candidates=True)
+            res.extend(out[0])
+            cands.append(out[2])
+            dets.append(out[3])
+        if not return_candidates:
+            return res
+
+        def merge(ds):
+            m = {}
+            for k, v in ds[0].items():
+                m[k] = torch.cat([d[k] for d in ds], 0) if isinstance(v, torch.Tensor) else v
+            return m
+        return res, None, merge(cands), merge(dets)
 
     def _to_instances(self, det, out_hw):
         counts = det["count"].cpu().tolist()

@@ -423,6 +423,33 @@ def test_batched_equals_single_image():
         assert torch.equal(r1.pred_boxes_covariance, res_b[i].pred_boxes_covariance)
 
 
+def test_chunked_pipelined_call_equals_one_call():
+    """infer_from_features(chunk_images=c) evaluates the batch chunk by chunk (bounded activation memory) and uploads
+    host-resident features of the next chunk on a copy stream meanwhile; results must be bit-identical to the
+    single call, for pinned-host and for device-resident features, and for a ragged last chunk."""
+    name = "mcdrop_pre_n4"
+    opts, mode, n_mc, seeds, hw, out_hw, seed, img = C.CASES[name]
+    cfg, pp, sds, _ = _oracle_case(name)
+    pred = build_predictor(cfg)
+    pred.load_weight_sets(sds[0])
+    per_img = [S.make_features(0, i, hw[0], hw[1]) for i in range(5)]
+    host = [torch.cat([f[l] for f in per_img], 0).pin_memory() for l in range(5)]
+    ref, _, ref_cand, ref_det = pred.infer_from_features(host, hw, out_hw, image0=20, seed=seed, return_candidates=True)
+    for feats in (host, [f.cuda() for f in host]):
+        for chunk in (2, 1):
+            got, _, cand, det = pred.infer_from_features(feats, hw, out_hw, image0=20, seed=seed, return_candidates=True,
+                                                         chunk_images=chunk)
+            assert len(got) == len(ref) == 5
+            assert torch.equal(det["count"], ref_det["count"]) and torch.equal(cand["count"], ref_cand["count"])
+            for a, b in zip(got, ref):
+                assert torch.equal(a.pred_boxes.tensor, b.pred_boxes.tensor)
+                assert torch.equal(a.scores, b.scores)
+                assert torch.equal(a.pred_classes, b.pred_classes)
+                assert torch.equal(a.pred_boxes_covariance, b.pred_boxes_covariance)
+    only = pred.infer_from_features(host, hw, out_hw, image0=20, seed=seed, chunk_images=3)      # list of Instances only
+    assert len(only) == 5 and torch.equal(only[4].scores, ref[4].scores)
+
+
 def test_reference_call_surface():
     """predictor(input_im) with the reference's input dict; invalid meta-architecture / mode raise
     ValueError as in probabilistic_inference.py:29-33,100-103."""
