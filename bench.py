@@ -173,7 +173,7 @@ def run_reference_arm(args, rank, world):
         if i >= args.warmup:
             vals.append(v)
     value = sum(vals) / len(vals)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": METRIC if args.n_mc == N_MC else METRIC.replace("N=30", "N=%d" % args.n_mc), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world),
@@ -373,7 +373,7 @@ def main():
             gbs = nbytes / (t_ms / 1000.0) / 1e9
             hbm_kernels[tag] = {"kernel": names[tag], "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                                 "frac": gbs / hbm_peak, "launches": cnt, "share_of_step": t_ms / ms}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": METRIC if args.n_mc == N_MC else METRIC.replace("N=30", "N=%d" % args.n_mc), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (fp16x3 split operands on tcgen05, fp32 accumulate)", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks,
