@@ -39,16 +39,17 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_layouts_match_header(tmp_path):
     from pod_compare_b200 import _cabi
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n",'
                    'sizeof(pod_dropout),sizeof(pod_conv_args),sizeof(pod_decode_args),sizeof(pod_nms_args),'
                    'offsetof(pod_conv_args,out2_pixel_stride),offsetof(pod_decode_args,out_anchor),offsetof(pod_nms_args,skip_post),'
-                   'sizeof(pod_merge_args),offsetof(pod_merge_args,out_count));return 0;}\n' % HEADER)
+                   'sizeof(pod_merge_args),offsetof(pod_merge_args,out_count),offsetof(pod_conv_args,map_live));return 0;}\n' % HEADER)
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [ctypes.sizeof(_cabi.Dropout), ctypes.sizeof(_cabi.ConvArgs), ctypes.sizeof(_cabi.DecodeArgs),
             ctypes.sizeof(_cabi.NmsArgs), _cabi.ConvArgs.out2_pixel_stride.offset, _cabi.DecodeArgs.out_anchor.offset,
-            _cabi.NmsArgs.skip_post.offset, ctypes.sizeof(_cabi.MergeArgs), _cabi.MergeArgs.out_count.offset]
+            _cabi.NmsArgs.skip_post.offset, ctypes.sizeof(_cabi.MergeArgs), _cabi.MergeArgs.out_count.offset,
+            _cabi.ConvArgs.map_live.offset]
     assert got == want
 
 
