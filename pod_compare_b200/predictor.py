@@ -80,6 +80,7 @@ class ProbabilisticPredictor:
         # (reference probabilistic_inference.py:216-267 loops over range(len-1)): the tower passes feeding
         # only those outputs are left out.  Results are unchanged; set False to evaluate them anyway.
         self.skip_unread_outputs = True
+        self.max_activation_bytes = 64e9  # auto-chunking budget of infer_from_features / predict_batch
         self._copy_stream = None          # host->device prefetch of the next chunk (infer_from_features chunk_images)
         self.rng_seed = int(self.cfg.SEED) if int(self.cfg.SEED) >= 0 else 0
         self.weight_sets = []
@@ -181,6 +182,12 @@ class ProbabilisticPredictor:
         if self._engine is None:
             raise _cabi.PodError("no weights loaded: call load_weight_sets(state_dicts) first")
         B = int(feats[0].shape[0])
+        if chunk_images is None and B > 1:
+            # keep the activation working set inside the budget (default 64 GB of the 180 GB): a batch of 64 images at
+            # N=30 would otherwise ask for 2 x 64 x 60 maps of 96x160x256 split pairs = 240 GB
+            auto = max(1, int(self.max_activation_bytes // self._activation_bytes_per_image(feats)))
+            if auto < B and not return_raw:
+                chunk_images = auto
         if chunk_images is not None and 0 < int(chunk_images) < B:
             if return_raw:
                 raise ValueError("return_raw is per chunk: call infer_from_features once per chunk")
@@ -217,6 +224,18 @@ class ProbabilisticPredictor:
         if return_raw or return_candidates:
             return res, (raw if return_raw else None), cand, det
         return res
+
+    def _activation_bytes_per_image(self, feats):
+        """Device bytes one image adds to a head pass: the two ping-pong activation buffers (maps x largest level x
+        256 channels x 4 B) plus the raw per-sample outputs (22-32 floats per anchor and sample)."""
+        m = self.model
+        mc = self.mc_dropout_enabled and self.num_mc_dropout_runs > 1
+        samples = self.num_mc_dropout_runs if mc else max(1, len(self.weight_sets))
+        maps = samples * (2 if (m.compute_cls_var or m.compute_bbox_cov) else 1) if mc else 1
+        hw = [int(f.shape[-2]) * int(f.shape[-1]) for f in feats]
+        anchors = sum(hw) * len(self.cfg.MODEL.ANCHOR_GENERATOR.ASPECT_RATIOS[0]) * len(self.cfg.MODEL.ANCHOR_GENERATOR.SIZES[0])
+        per_anchor = 2 * m.num_classes + 4 + max(4, m.bbox_cov_dims)
+        return 2 * maps * max(hw) * 256 * 4 + max(hw) * 256 * 4 + samples * anchors * per_anchor * 4
 
     def _infer_chunked(self, feats, image_hw, out_hw, image0, seed, return_candidates, chunk):
         B = int(feats[0].shape[0])

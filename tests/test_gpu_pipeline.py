@@ -448,6 +448,11 @@ def test_chunked_pipelined_call_equals_one_call():
                 assert torch.equal(a.pred_boxes_covariance, b.pred_boxes_covariance)
     only = pred.infer_from_features(host, hw, out_hw, image0=20, seed=seed, chunk_images=3)      # list of Instances only
     assert len(only) == 5 and torch.equal(only[4].scores, ref[4].scores)
+    # automatic chunking: with a budget of two images' activations the same call runs as chunks of two
+    pred.max_activation_bytes = 2.5 * pred._activation_bytes_per_image(host)
+    auto = pred.infer_from_features(host, hw, out_hw, image0=20, seed=seed)
+    assert len(auto) == 5 and all(torch.equal(a.scores, b.scores) and torch.equal(a.pred_boxes.tensor, b.pred_boxes.tensor)
+                                  for a, b in zip(auto, ref))
 
 
 def test_reference_call_surface():
