@@ -405,6 +405,32 @@ def test_unread_last_sample_outputs_are_skipped_without_changing_results(name):
         assert torch.equal(a.pred_boxes_covariance, b.pred_boxes_covariance)
 
 
+@pytest.mark.parametrize("name", ["mcdrop_pre_n4", "regclsvar_std", "bayesod_mc_n3", "mcdrop_post_n3"])
+def test_no_anchor_above_threshold_gives_empty_instances(name):
+    """with the reference's own initialisation (cls_score bias -log(99), tiny logit weights) every score is
+    ~0.01 < SCORE_THRESH_TEST = 0.05, so no anchor survives.  The whole path must return empty, well-formed
+    Instances (and the oracle agrees) instead of failing on zero-sized work, in every mode and in a batch."""
+    opts, mode, n_mc, seeds, hw, out_hw, seed, img = C.CASES[name]
+    cfg = C.build_cfg(name)
+    pp = O.PathParams.from_cfg(cfg)
+    sd = S.make_head_state_dict(seeds[0], num_classes=pp.num_classes, use_dropout=pp.use_dropout, cls_var=pp.cls_var,
+                                bbox_cov=pp.bbox_cov, cov_dims=pp.cov_dims, logit_scale=0.01, logit_bias=-4.595)
+    feats = S.make_features(0, img, hw[0], hw[1])
+    feats2 = [torch.cat([f, f], 0) for f in feats]
+    pred = build_predictor(cfg)
+    pred.load_weight_sets(sd)
+    res = pred.infer_from_features(feats2, hw, out_hw, image0=img, seed=seed)
+    assert len(res) == 2
+    for inst in res:
+        assert len(inst) == 0
+        assert tuple(inst.pred_boxes.tensor.shape) == (0, 4) and tuple(inst.pred_boxes_covariance.shape) == (0, 4, 4)
+        assert tuple(inst.pred_cls_probs.shape) == (0, pp.num_classes) and inst.pred_classes.dtype == torch.int64
+    if not C.is_post_nms(name):
+        torch.set_num_threads(8)
+        ref = O.predict(feats, [O.unpack_head(sd, pp)], pp, mode, hw, out_hw=out_hw, n_mc=n_mc, seed=seed, image=img)
+        assert ref.boxes.shape[0] == 0
+
+
 def test_batched_equals_single_image():
     """B images in one call == B single-image calls (a batch is B independent problems)."""
     name = "mcdrop_pre_n4"
