@@ -150,7 +150,8 @@ extern "C" __attribute__((visibility("default"))) int pod_mask_expand_split(cons
   if (live_reps == 0) live_reps = d->samples * d->passes;
   const int64_t qpm = (int64_t)HW * C / 8;
   const int64_t total = qpm * NB_in;
-  const int grid = (int)((total + 255) / 256 < (int64_t)pod_num_sms() * 16 ? (total + 255) / 256 : (int64_t)pod_num_sms() * 16);
+  // 39 registers x 256 threads: six CTAs are resident per SM; a grid of exactly that many leaves no partial last wave
+  const int grid = (int)((total + 255) / 256 < (int64_t)pod_num_sms() * 6 ? (total + 255) / 256 : (int64_t)pod_num_sms() * 6);
   k_mask_expand<<<grid, 256, 0, (cudaStream_t)stream>>>(x, qpm, NB_in, *d, scale, pod_dropout_threshold(d->p),
                                                         pod_dropout_scale(d->p), pod_key(d->seed, POD_STREAM_DROPOUT),
                                                         (__half*)dst_hi, (__half*)dst_lo, live_reps);
@@ -208,7 +209,7 @@ extern "C" __attribute__((visibility("default"))) int pod_sample_mean_q1(const f
   const int64_t total = (int64_t)B * n;
   if (n % 4 == 0 && ((uintptr_t)x | (uintptr_t)out) % 16 == 0) {
     const int64_t total4 = total / 4;
-    const int64_t want = (total4 + 255) / 256, cap = (int64_t)pod_num_sms() * 8;
+    const int64_t want = (total4 + 255) / 256, cap = (int64_t)pod_num_sms() * 6;   // six resident CTAs per SM (38 registers)
     k_sample_mean_q1_v4<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(x), S, n / 4, total4, reinterpret_cast<float4*>(out));
     POD_LAUNCH_CHECK();
