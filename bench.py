@@ -9,7 +9,7 @@ Q1 means -> scores/top-k -> decode + aleatoric/epistemic covariance -> NMS -> re
 is upstream of the rebuilt path and is not part of the step.
 
   python bench.py --gpus N --steps K --warmup W            (N>1 under torchrun, one rank per GPU)
-  python bench.py --impl reference ...                      CPU arm: the oracle port of the same path
+  python bench.py --impl reference ...                      CPU arm: the reference's own predictor on the host cores
 """
 import argparse
 import gc
@@ -22,6 +22,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+
+if "reference" in sys.argv and "--impl" in sys.argv:
+    # the reference arm is the reference's CPU path: its post-processing picks "cuda if available" at import time
+    # (inference_utils.py:9), so the GPUs are hidden from this process before torch initialises
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
 
 import torch
 
@@ -126,61 +131,106 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_path_rate(n_mc, samples_timed=1, threads=None, repeats=1):
-    """Times the oracle port (oracle/podref.py: the reference's algorithm in fp32 torch CPU ops) on the
-    host cores for ONE image: `samples_timed` MC samples of the head + the full post-processing, and
-    extrapolates linearly to n_mc samples (the head loop is n_mc identical iterations,
-    probabilistic_retinanet.py:104-108,517-523).  Returns (images/s, cores, description)."""
-    from oracle import podref as O
+REF_TIME_BUDGET_S = 240.0      # the reference arm stops adding timed steps once this much wall time is spent
+
+
+def reference_steps(n_mc, workload, steps, warmup, threads=None, budget_s=REF_TIME_BUDGET_S):
+    """The reference arm: the reference's OWN `build_predictor(cfg)` -> `predictor(input_im)`
+    (src/apply_net.py:82-91, probabilistic_inference.py:86-111) on the host cores, one FULL image per step at the
+    workload's sample count -- no extrapolation.  The reference modules come unmodified from /root/reference or
+    from the byte-for-byte staged copy under oracle/_ref (oracle/make_ref.py); its un-vendored detectron2 dependency
+    is the stand-in of oracle/ref_shim, whose backbone hands the synthetic FPN maps to the unmodified forward()
+    (the ResNet-FPN backbone is outside the step in both arms).  torch's own generator drives dropout and sampling
+    (stock code path).  Falls back to the oracle port (oracle/podref.py, kind "port") only if no reference sources
+    are on the machine.  Returns (per-step seconds list, cores, kind, description)."""
     from pod_compare_b200 import synthetic as S
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    cfg = build_cfg(n_mc)
-    pp = O.PathParams.from_cfg(cfg)
-    sd = S.make_head_state_dict(0, num_classes=7, use_dropout=True, cls_var=True, bbox_cov=True)
-    hw = O.unpack_head(sd, pp)
-    feats = S.make_features(0, 0, HEIGHT, WIDTH)
-    anchors = O.make_anchors([tuple(f.shape[-2:]) for f in feats], pp)
-    drop = O.DropoutSource("torch", pp.dropout_rate)
+    cfg = build_cfg(n_mc, workload)
+    desc_w, _, mc, members = WORKLOADS[workload]
+    m = cfg.MODEL.PROBABILISTIC_MODELING
+    use_dropout, cls_var, bbox_cov = m.DROPOUT_RATE != 0.0, m.CLS_VAR_LOSS.NAME != "none", m.BBOX_COV_LOSS.NAME != "none"
+    sds = [S.make_head_state_dict(1000 * e, num_classes=7, use_dropout=use_dropout, cls_var=cls_var, bbox_cov=bbox_cov)
+           for e in range(members)]
     import torchvision          # first use pulls in seconds of lazy imports: keep them out of the timing
     torchvision.ops.nms(torch.tensor([[0.0, 0.0, 1.0, 1.0]]), torch.tensor([1.0]), 0.5)
-    best_head, best_post = None, None
-    with torch.no_grad():
-        for _ in range(repeats):
+    from oracle import ref_runner as R
+    if R.reference_available():
+        kind = "reference"
+        pred = R.build_reference_predictor(cfg, sds if members > 1 else sds[0])
+
+        def one_image(i):
+            feats = S.make_member_features(members, i, HEIGHT, WIDTH) if members > 1 else S.make_features(0, i, HEIGHT, WIDTH)
+            R._set_features(pred, feats)
+            input_im = [{"image": torch.zeros((3, HEIGHT, WIDTH), dtype=torch.uint8), "height": HEIGHT, "width": WIDTH,
+                         "image_id": i}]
             t0 = time.perf_counter()
-            outs = [O.head_outputs(feats, hw, pp, drop, sample=s) for s in range(samples_timed)]
-            t_head = (time.perf_counter() - t0) / samples_timed
-            outs_n = [outs[i % samples_timed] for i in range(max(3, samples_timed))]   # epistemic branch needs >1
+            with torch.no_grad():
+                out = pred(input_im)
+            return time.perf_counter() - t0, len(out)
+        src = "unmodified reference modules from %s via oracle/ref_shim" % R.REFERENCE_ROOT
+    else:
+        kind = "port"
+        from oracle import podref as O
+        pp = O.PathParams.from_cfg(cfg)
+        hws = [O.unpack_head(sd, pp) for sd in sds]
+        mode = cfg.PROBABILISTIC_INFERENCE.INFERENCE_MODE
+
+        def one_image(i):
+            feats = S.make_member_features(members, i, HEIGHT, WIDTH) if members > 1 else S.make_features(0, i, HEIGHT, WIDTH)
             t0 = time.perf_counter()
-            cand = O.anchorwise(outs_n, anchors, pp, 0, 0, normal_mode="torch")
-            det = O.standard_nms_post(cand, pp, (HEIGHT, WIDTH))
-            O.detector_postprocess(det, HEIGHT, WIDTH)
-            t_post = time.perf_counter() - t0
-            best_head = t_head if best_head is None else min(best_head, t_head)
-            best_post = t_post if best_post is None else min(best_post, t_post)
-    per_image = n_mc * best_head + best_post
-    desc = ("1 image: %d MC sample(s) of the head timed (%.2f s each) + full post-processing (%.2f s), "
-            "extrapolated to N=%d: %.1f s/image" % (samples_timed, best_head, best_post, n_mc, per_image))
-    return 1.0 / per_image, threads, desc
+            with torch.no_grad():
+                out = O.predict(feats, hws, pp, mode, (HEIGHT, WIDTH), n_mc=n_mc if mc else 1, seed=0, image=i,
+                                dropout_mode="torch")
+            return time.perf_counter() - t0, int(out.boxes.shape[0])
+        src = "oracle/podref.py (no reference sources on this machine)"
+    for w in range(min(warmup, 1)):
+        one_image(1000 + w)                     # untimed; one image pages in every code path
+    times, dets, t_start = [], [], time.perf_counter()
+    for k in range(steps):
+        t, n = one_image(k)
+        times.append(t)
+        dets.append(n)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    desc = ("%s; one full 1280x720 image per step through build_predictor(cfg) -> predictor(input_im), %s, %d torch threads; "
+            "%d of %d requested steps timed (wall-time budget %.0f s), %.2f s per image, no extrapolation; detections per "
+            "image %s" % (src, ("N=%d MC-dropout samples" % n_mc) if mc else ("E=%d members" % members if members > 1 else "single forward"),
+                          threads, len(times), steps, budget_s, sum(times) / len(times), dets[:4]))
+    return times, threads, kind, desc
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    vals = []
-    for i in range(args.warmup + args.steps):
-        v, cores, desc = cpu_path_rate(args.n_mc, samples_timed=1)
-        if i >= args.warmup:
-            vals.append(v)
-    value = sum(vals) / len(vals)
-    line = {"impl": "reference", "metric": METRIC if args.n_mc == N_MC else METRIC.replace("N=30", "N=%d" % args.n_mc), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
+    times, cores, kind, desc = reference_steps(args.n_mc, args.workload, args.steps, args.warmup)
+    per_image = sum(times) / len(times)
+    value = 1.0 / per_image
+    line = {"impl": "reference", "metric": METRIC if args.n_mc == N_MC else METRIC.replace("N=30", "N=%d" % args.n_mc),
+            "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times), "steps_requested": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 * per_image, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if args.workload != "mc_pre":
+        line["metric"] = "images/sec, side workload (not the BASELINE headline)"
     print(json.dumps(line))
+
+
+def cpu_baseline_subprocess(args):
+    """cpu_baseline leg of the GPU arm: one image through the reference arm in a child process (the GPUs are hidden
+    from it, see the top of this file)."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--n-mc", str(args.n_mc), "--workload", args.workload, "--batch", str(args.batch)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=1800)
+    for ln in reversed(out.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    raise RuntimeError("reference arm failed: %s" % out.stderr[-2000:])
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -381,9 +431,8 @@ def main():
             "gpu_launches": launches, "roofline": roof, "hbm_kernels": hbm_kernels}
     if args.workload != "mc_pre":
         line["metric"] = "images/sec, side workload (not the BASELINE headline)"
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "mc_pre":
-        v, cores, desc = cpu_path_rate(args.n_mc, samples_timed=2)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_subprocess(args)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -27,12 +27,19 @@
 extern "C" {
 #endif
 
-#define POD_ABI_VERSION 1
+#define POD_ABI_VERSION 2
 
 const char* pod_last_error(void);
 int pod_version(void);
 /* 1 if the current device can run the sm_100a kernels (compute capability 10.x). */
 int pod_device_ok(void);
+/* Device-side error word of the library, read and cleared (this call synchronises the device).  0 = ok;
+ * 1..99 = a bounded mbarrier wait of the tcgen05 kernels expired (the code names the wait); 100 = a hidden tower
+ * activation left the fp16 split range (|x * out_scale| > 65504: the reference computes in fp32 and has no such
+ * limit, so the condition is reported instead of propagating inf / NaN); 101 = the same in pod_mask_expand_split;
+ * 102 = non-finite input feature (pod_absmax_accumulate).  The product path (predictor.infer_from_features) calls
+ * it once per inference call and raises PodError on a non-zero word. */
+int pod_status(int* status_host);
 
 /* ---- counter-based random streams (parity contract with oracle/philox.py) -------------------
  * Replace torch's generator at the three places the reference draws randomness:
@@ -51,6 +58,14 @@ int pod_philox_box_normals(float* out_draws_m_4, const int64_t* anchor_ids, int 
  * -> channels-last fp16 split pair. */
 int pod_nchw_to_nhwc_split(const float* src_nchw, int NB, int C, int H, int W, float scale,
                            void* dst_hi, void* dst_lo, void* stream);
+/* fp16 split scale of the input maps without a host round trip: pod_absmax_accumulate folds max|x| of a tensor into
+ * *amax_bits (device word, zero it first; bit pattern of a non-negative float), pod_pow2_scale_from_absmax writes
+ * min(max_scale, largest power of two s with amax * s <= target) to *scale_dev, and pod_nchw_to_nhwc_split_dev /
+ * pod_conv_args.in_scale_dev read it from device memory. */
+int pod_absmax_accumulate(const float* x, int64_t n, uint32_t* amax_bits, void* stream);
+int pod_pow2_scale_from_absmax(const uint32_t* amax_bits, float max_scale, float target, float* scale_dev, void* stream);
+int pod_nchw_to_nhwc_split_dev(const float* src_nchw, int NB, int C, int H, int W, const float* scale_dev,
+                               void* dst_hi, void* dst_lo, void* stream);
 /* Same layout change, fp32 out (input of the SIMT cross-check convolution). */
 int pod_nchw_to_nhwc_f32(const float* src_nchw, int NB, int C, int H, int W, float* dst, void* stream);
 /* nn.Conv2d weight (Cout, Cin, 3, 3) fp32 -> K-major GEMM operand rows [Cout_pad][9*Cin] with
@@ -133,17 +148,21 @@ typedef struct pod_conv_args {
    * "mean" runs over range(len-1); only box_delta of the last sample is used, :326-331). */
   int map_group;
   int map_live;
+  /* Optional device-resident input scale (a power of two written by pod_pow2_scale_from_absmax); when non-NULL it
+   * replaces in_scale.  Not available for the weights-as-A output convolutions (their inputs are tower activations
+   * with the fixed scale). */
+  const float* in_scale_dev;
 } pod_conv_args;
 int pod_conv3x3_tc(const pod_conv_args* a, void* stream);
 /* Channels per pipeline stage of the tcgen05 kernel: 64 (SWIZZLE_128B operand tiles, default) or
  * 32 (SWIZZLE_64B, deeper pipeline).  Process-wide tuning knob; results are identical. */
 int pod_conv3x3_tc_set_kblock(int bk);
-/* 3x3 taps summed inside the tensor core before the partial sum is added in fp32 round-to-nearest by
- * the epilogue warps: 1 (default, most accurate), 3 or 9 (single chain; tcgen05 accumulates with
- * truncation, which drifts ~2e-5 relative over the 2304-long reduction). */
+/* Accumulation chunk = how much of the K loop is summed inside the tensor core (fp32 TMEM, truncating adds) before
+ * the epilogue warps add the partial sum in fp32 round-to-nearest.  Two knobs, ONE wins: chunk_kblocks (default 12
+ * K-blocks of 64 channels = 3 taps) is used whenever it is > 0 and divides the K-block count of the convolution;
+ * only otherwise (or after pod_conv3x3_tc_set_chunk_kblocks(0)) the taps setting applies (default 1 tap per chunk;
+ * 3 or 9 = coarser; 9 = a single 2304-long chain, which drifts ~7e-6 relative without the compensation below). */
 int pod_conv3x3_tc_set_chunk_taps(int taps);
-/* Finer control: K-blocks per accumulation chunk (default 12 = 768 channels = 3 taps; 0 = use the taps
- * setting); ignored for a convolution whose K-block count it does not divide. */
 int pod_conv3x3_tc_set_chunk_kblocks(int kb);
 /* Compensation of the tensor core's accumulate-with-truncation: expected loss per MMA accumulation in fp32 ulps
  * of the running sum (default 0.27, measured; 0 = off).  The epilogue scale is multiplied by 1 + ulps * (MMAs per TMEM chain) * 2^-24. */
@@ -159,9 +178,13 @@ int pod_conv3x3_tc_set_wt(int on);
 int pod_conv3x3_tc_set_halo(int mode);
 /* 256-output-channel convolutions on CTA pairs (tcgen05 cta_group::2, default on) or on single CTAs. */
 int pod_conv3x3_tc_set_pair(int on);
-/* Device-side error word of the last tcgen05 launch on this thread (0 = ok; set when a bounded
- * barrier wait expired).  Host pointer out. */
+/* Device-side error word of the tcgen05 kernels only (see pod_status).  Host pointer out. */
 int pod_conv3x3_tc_status(int* status_host);
+/* Test hooks: the cycle budget of every bounded mbarrier wait (default ~2 s; <= 0 restores it) and a fault
+ * injection that makes the TMA producer of the first CTA / CTA pair skip its loads, so that the bounded waits of that
+ * CTA expire and the error path (pod_status != 0 -> PodError in the predictor) can be exercised. */
+int pod_conv3x3_tc_set_wait_limit(long long cycles);
+int pod_conv3x3_tc_debug_fault(int on);
 
 /* Plain fp32 SIMT convolution with the same semantics (cross-check of the tensor-core kernel;
  * not on the product path). in (NB,H,W,Cin) fp32, w from pod_pack_conv_weight_f32. */
@@ -225,6 +248,10 @@ typedef struct pod_decode_args {
   float* out_probs;
   int* out_count;
   int* out_anchor;
+  /* regression weights of the SAMPLED decode (inference_utils.py:510-547 SampleBox2BoxTransform, built from
+   * cfg.MODEL.RPN.BBOX_REG_WEIGHTS at probabilistic_inference.py:175-176) -- the deterministic / per-sample decodes
+   * above use the RetinaNet weights (wx..wh).  All four 0 = same as wx..wh. */
+  float swx, swy, sww, swh;
 } pod_decode_args;
 int pod_decode_cov(const pod_decode_args* a, void* stream);
 

@@ -51,9 +51,26 @@ CASES = {
                           (96, 160), (96, 160), 23, 12),
     "coco80_std": (_VAR + _mode("standard_nms") + ["MODEL.RETINANET.NUM_CLASSES", 80], "standard_nms", 1, [0],
                    (64, 64), (64, 64), 24, 13),
+    # MC_DROPOUT.ENABLE with NUM_RUNS == 1: the reference keeps the model in train() (:52-56), so the single forward
+    # has active dropout (mean / variance heads from independently masked tower passes) and no epistemic term
+    "mcdrop_single": (_VAR + _DROP + _mode("standard_nms") + _mc(1), "standard_nms", 1, [2000], (96, 160), (96, 160), 25, 14),
+    # the sampled (aleatoric) decode uses MODEL.RPN.BBOX_REG_WEIGHTS, the deterministic one MODEL.RETINANET.BBOX_REG_WEIGHTS
+    "regclsvar_rpnw": (_VAR + _mode("standard_nms") + ["MODEL.RPN.BBOX_REG_WEIGHTS", (2.0, 2.0, 1.5, 1.5)], "standard_nms", 1,
+                       [1000], (96, 160), (96, 160), 26, 15),
     "fullcov_mc_n3": (_VAR + _FULL + _DROP + _mode("mc_dropout_ensembles") + _mc(3), "mc_dropout_ensembles", 3, [3000],
                       (96, 160), (96, 160), 19, 8),
 }
+
+
+def case_features(name):
+    """Synthetic FPN maps of a case.  Ensemble cases get ONE FEATURE SET PER MEMBER (correlated but different, synthetic.make_member_features):
+    each member of the reference is a full model with its own backbone (probabilistic_inference.py:58-77,499-501),
+    so the members never see the same feature maps."""
+    from pod_compare_b200 import synthetic as S
+    opts, mode, n_mc, seeds, hw, out_hw, seed, img = CASES[name]
+    if mode == "ensembles":
+        return S.make_member_features(len(seeds), img, hw[0], hw[1])
+    return S.make_features(0, img, hw[0], hw[1])
 
 
 def build_cfg(name):
@@ -64,6 +81,14 @@ def build_cfg(name):
     cfg.MODEL.DEVICE = "cpu"
     cfg.freeze()
     return cfg
+
+
+def is_mc_single(name):
+    """MC-dropout enabled with a single run: dropout active in the one forward, no sample aggregation."""
+    opts, mode, n_mc = CASES[name][0], CASES[name][1], CASES[name][2]
+    enabled = any(isinstance(o, str) and o == "PROBABILISTIC_INFERENCE.MC_DROPOUT.ENABLE" for o in opts)
+    has_drop = any(isinstance(o, str) and o == "MODEL.PROBABILISTIC_MODELING.DROPOUT_RATE" for o in opts)
+    return enabled and has_drop and n_mc == 1 and mode != "ensembles"
 
 
 def is_post_nms(name):

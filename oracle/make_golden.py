@@ -2,7 +2,7 @@
 
 Run in the build container (where /root/reference exists):
 
-    python -m oracle.make_golden
+    python -m oracle.make_golden [case names ... | planted]
 
 For every case of oracle/cases.py the reference's own `build_predictor(cfg)` /
 `predictor(input_im)` (src/probabilistic_inference/probabilistic_inference.py:20-111) is run on
@@ -29,6 +29,8 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 
 
 def feats_checksum(feats):
+    if isinstance(feats[0], (list, tuple)):
+        feats = [f for fs in feats for f in fs]
     return np.array([float(f.double().abs().sum()) for f in feats])
 
 
@@ -45,7 +47,7 @@ def model_case(name):
     opts, mode, n_mc, seeds, hw, out_hw, seed, img = C.CASES[name]
     cfg, pp, sds = state_dicts_for(name)
     pred = R.build_reference_predictor(cfg, sds if len(sds) > 1 else sds[0])
-    feats = S.make_features(0, img, hw[0], hw[1])
+    feats = C.case_features(name)
     final, _ = R.run_reference(pred, feats, hw, out_hw=out_hw, seed=seed, image_idx=img, stage="final")
     if C.is_post_nms(name):
         d = {"final_" + k: v for k, v in R.instances_to_arrays(final).items()}
@@ -110,9 +112,12 @@ def main():
         sys.exit("reference tree not available; fixtures can only be regenerated in the build container")
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    for name in C.CASES:
-        model_case(name)
-    planted_cases()
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    for name in (only or C.CASES):
+        if name != "planted":
+            model_case(name)
+    if not only or "planted" in only:
+        planted_cases()
 
 
 if __name__ == "__main__":

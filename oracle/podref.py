@@ -9,7 +9,7 @@ PARITY PIN: the reference ships no tests or golden vectors, s
 restatement is pinned against OUTPUTS OF THE REFERENCE ITSELF: oracle/make_golden.py runs the
 unmodified reference modules (through oracle/ref_runner.py) on seeded synthetic inputs and
 commits the results under tests/golden/; tests/test_oracle_golden.py requires this file to
-reproduce them, and tests/test_oracle_vs_reference.py re-runs the live comparison whenever
+reproduce them, and tests/test_oracle_live_reference.py re-runs the live comparison whenever
 /root/reference is present.
 
 Reference lines followed (relative to /root/reference/src):
@@ -60,7 +60,8 @@ class PathParams:
     score_thresh: float = 0.05
     nms_thresh: float = 0.5
     max_dets: int = 100
-    reg_weights: tuple = (1.0, 1.0, 1.0, 1.0)
+    reg_weights: tuple = (1.0, 1.0, 1.0, 1.0)          # MODEL.RETINANET.BBOX_REG_WEIGHTS -> apply_deltas
+    sample_reg_weights: tuple = (1.0, 1.0, 1.0, 1.0)   # MODEL.RPN.BBOX_REG_WEIGHTS -> SampleBox2BoxTransform (:175-176)
     affinity: float = 0.9
     box_merge: str = "bayesian_inference"
     cls_merge: str = "max_score"
@@ -93,6 +94,7 @@ class PathParams:
             nms_thresh=cfg.MODEL.RETINANET.NMS_THRESH_TEST,
             max_dets=cfg.TEST.DETECTIONS_PER_IMAGE,
             reg_weights=tuple(cfg.MODEL.RETINANET.BBOX_REG_WEIGHTS),
+            sample_reg_weights=tuple(cfg.MODEL.RPN.BBOX_REG_WEIGHTS),
             affinity=pi.AFFINITY_THRESHOLD,
             box_merge=pi.BAYES_OD.BOX_MERGE_MODE,
             cls_merge=pi.BAYES_OD.CLS_MERGE_MODE,
@@ -378,7 +380,7 @@ def anchorwise(outputs_list, anchors, pp: PathParams, seed=0, image=0, keep_diag
         draws = delta + torch.matmul(L, eps.unsqueeze(-1)).squeeze(-1)                  # loc + L eps
         draws = torch.transpose(torch.transpose(draws, 0, 1), 1, 2)                     # (M,4,S)
         anc_s = torch.repeat_interleave(anc.unsqueeze(2), S, dim=2)
-        boxes, cov = mean_covariance(apply_samples_deltas(draws, anc_s, pp.reg_weights))
+        boxes, cov = mean_covariance(apply_samples_deltas(draws, anc_s, pp.sample_reg_weights))
         if isinstance(all_epi[0], torch.Tensor):
             cov += torch.cat(all_epi)
     else:
@@ -640,17 +642,25 @@ def detections_to_json(d: Detections, img_id, cat_mapping):
 # whole path, one image:  features -> detections   (predictor.__call__, :86-111)
 # --------------------------------------------------------------------------------------
 def predict(feats, weight_sets, pp: PathParams, mode, image_hw, out_hw=None, n_mc=1, seed=0, image=0,
-            dropout_mode="philox", nms_impl="torchvision", return_candidates=False, keep_diag=False, post_nms=False):
+            dropout_mode="philox", nms_impl="torchvision", return_candidates=False, keep_diag=False, post_nms=False,
+            mc_single=False):
     """mode: 'standard_nms' | 'mc_dropout_ensembles' (pre_nms) | 'ensembles' (pre_nms) | 'bayes_od' |
     'anchor_statistics'.
     weight_sets: list of unpacked heads (len E for 'ensembles', else 1). n_mc>1 enables MC-dropout
     (model.train(), probabilistic_inference.py:52-56)."""
     out_hw = out_hw or image_hw
-    level_hw = [tuple(f.shape[-2:]) for f in feats]
+    per_member = isinstance(feats[0], (list, tuple))      # ensembles: feats[e][l], one feature set per member
+    level_hw = [tuple(f.shape[-2:]) for f in (feats[0] if per_member else feats)]
     anchors = make_anchors(level_hw, pp)
     if mode == "ensembles":
+        # every member is a full model with its own backbone (probabilistic_inference.py:58-77,499-501)
         drop = DropoutSource("off", 0.0)
-        outs = [head_outputs(feats, hw, pp, drop) for hw in weight_sets]
+        outs = [head_outputs(feats[e] if per_member else feats, hw, pp, drop) for e, hw in enumerate(weight_sets)]
+    elif mc_single:
+        # MC_DROPOUT.ENABLE with NUM_RUNS == 1: the model stays in train() (:52-56) and the single forward (:272-273)
+        # has active dropout; no epistemic term
+        drop = DropoutSource(dropout_mode, pp.dropout_rate, seed, image)
+        outs = [head_outputs(feats, weight_sets[0], pp, drop, sample=0)]
     elif n_mc > 1:
         drop = DropoutSource(dropout_mode, pp.dropout_rate, seed, image)
         outs = [head_outputs(feats, weight_sets[0], pp, drop, sample=s) for s in range(n_mc)]

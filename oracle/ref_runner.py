@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE (oracle) -- runs the UNMODIFIED reference predictor on CPU.
 
-Only usable where /root/reference exists (the build container).  It puts the shim
+Usable where /root/reference exists (the build container) or where oracle/make_ref.py staged the reference's
+four hot-path files under oracle/_ref (git-ignored; travels to the GPU box).  It puts the shim
 packages of oracle/ref_shim (detectron2 / fvcore stand-ins) and /root/reference/src on
 sys.path, imports the reference's own modules
 
@@ -26,12 +27,24 @@ import torch
 
 from oracle import philox
 
-REFERENCE_ROOT = os.environ.get("POD_REFERENCE_ROOT", "/root/reference")
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shim")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIM = os.path.join(_HERE, "ref_shim")
+
+
+def _reference_root():
+    """/root/reference in the build container; on the GPU box the byte-for-byte staged copy of the reference's four
+    hot-path files under oracle/_ref (oracle/make_ref.py)."""
+    for root in (os.environ.get("POD_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if root and os.path.isfile(os.path.join(root, "src", "probabilistic_inference", "probabilistic_inference.py")):
+            return root
+    return None
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "probabilistic_inference"))
+    return REFERENCE_ROOT is not None
 
 
 _mods = {}
@@ -42,7 +55,7 @@ def load_reference():
     if _mods:
         return _mods
     if not reference_available():
-        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+        raise RuntimeError("reference sources not present (neither /root/reference nor oracle/_ref)")
     src = os.path.join(REFERENCE_ROOT, "src")
     for p in (src, _SHIM):
         if p in sys.path:
@@ -55,6 +68,9 @@ def load_reference():
     _mods["modeling_utils"] = importlib.import_module("probabilistic_modeling.modeling_utils")
     _mods["inference_utils"] = importlib.import_module("probabilistic_inference.inference_utils")
     _mods["inference"] = importlib.import_module("probabilistic_inference.probabilistic_inference")
+    # the reference picks its post-processing device at import time (inference_utils.py:9: cuda if available); the oracle
+    # is the reference's CPU path, also on a machine that has a GPU
+    _mods["inference_utils"].device = torch.device("cpu")
     return _mods
 
 
@@ -165,11 +181,17 @@ def build_reference_predictor(cfg, state_dicts):
 
 
 def _set_features(predictor, feats):
+    """feats: list over levels (shared), or -- ensembles -- a list over members of lists over levels: every member
+    of the reference is a full model with its own backbone and therefore its own feature maps
+    (probabilistic_inference.py:58-77,499-501)."""
     names = predictor.model.in_features
-    cur = {n: f for n, f in zip(names, feats)}
-    predictor.model.backbone.current = cur
-    for m in predictor.model_list:
-        m.backbone.current = cur
+    per_member = isinstance(feats[0], (list, tuple))
+    sets = feats if per_member else [feats]
+    predictor.model.backbone.current = {n: f for n, f in zip(names, sets[0])}
+    if per_member:
+        assert len(sets) == len(predictor.model_list), (len(sets), len(predictor.model_list))
+    for e, m in enumerate(predictor.model_list):
+        m.backbone.current = {n: f for n, f in zip(names, sets[e if per_member else 0])}
 
 
 def run_reference(predictor, feats, image_hw, out_hw=None, seed=1, image_idx=0, stage="final"):
@@ -183,6 +205,8 @@ def run_reference(predictor, feats, image_hw, out_hw=None, seed=1, image_idx=0, 
     input_im = [{"image": torch.zeros((3, H, W), dtype=torch.uint8), "height": out_hw[0],
                  "width": out_hw[1], "image_id": image_idx}]
     _set_features(predictor, feats)
+    if isinstance(feats[0], (list, tuple)):
+        feats = feats[0]
     head = predictor.model.head
     per_entry = 8 + (4 if head.compute_cls_var else 0) + (4 if head.compute_bbox_cov else 0)
     A = 9

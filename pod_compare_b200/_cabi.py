@@ -10,7 +10,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpodb200.so")
 
 EXPORTS = [
-    "pod_last_error", "pod_version", "pod_device_ok",
+    "pod_last_error", "pod_version", "pod_device_ok", "pod_status",
+    "pod_absmax_accumulate", "pod_pow2_scale_from_absmax", "pod_nchw_to_nhwc_split_dev",
+    "pod_conv3x3_tc_set_wait_limit", "pod_conv3x3_tc_debug_fault",
     "pod_philox_dropout_mask", "pod_philox_logit_normals", "pod_philox_box_normals",
     "pod_nchw_to_nhwc_split", "pod_nchw_to_nhwc_f32", "pod_pack_conv_weight", "pod_pack_conv_weight_f32",
     "pod_mask_expand_split", "pod_conv3x3_tc", "pod_conv3x3_tc_set_kblock", "pod_conv3x3_tc_set_chunk_taps", "pod_conv3x3_tc_set_chunk_kblocks", "pod_conv3x3_tc_set_pair", "pod_conv3x3_tc_set_halo", "pod_conv3x3_tc_set_wt", "pod_conv3x3_tc_set_trunc_comp", "pod_conv3x3_tc_status",
@@ -38,7 +40,8 @@ class ConvArgs(C.Structure):
                 ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_scale", C.c_float), ("out_f32", C.c_void_p),
                 ("out_map_stride", C.c_int64), ("out_pixel_stride", C.c_int64), ("drop", Dropout),
                 ("out2_f32", C.c_void_p), ("split_col", C.c_int), ("out2_map_stride", C.c_int64),
-                ("out2_pixel_stride", C.c_int64), ("map_group", C.c_int), ("map_live", C.c_int)]
+                ("out2_pixel_stride", C.c_int64), ("map_group", C.c_int), ("map_live", C.c_int),
+                ("in_scale_dev", C.c_void_p)]
 
 
 class DecodeArgs(C.Structure):
@@ -50,7 +53,7 @@ class DecodeArgs(C.Structure):
                 ("image0", C.c_int), ("runs", C.c_int), ("wx", C.c_float), ("wy", C.c_float), ("ww", C.c_float), ("wh", C.c_float),
                 ("out_boxes", C.c_void_p), ("out_cov", C.c_void_p), ("out_scores", C.c_void_p),
                 ("out_classes", C.c_void_p), ("out_probs", C.c_void_p), ("out_count", C.c_void_p),
-                ("out_anchor", C.c_void_p)]
+                ("out_anchor", C.c_void_p), ("swx", C.c_float), ("swy", C.c_float), ("sww", C.c_float), ("swh", C.c_float)]
 
 
 class NmsArgs(C.Structure):
@@ -114,6 +117,12 @@ def load_library():
     lib.pod_conv3x3_tc_set_wt.argtypes = [C.c_int]
     lib.pod_conv3x3_tc_set_trunc_comp.argtypes = [C.c_float]
     lib.pod_conv3x3_tc_status.argtypes = [C.POINTER(C.c_int)]
+    lib.pod_status.argtypes = [C.POINTER(C.c_int)]
+    lib.pod_conv3x3_tc_set_wait_limit.argtypes = [C.c_longlong]
+    lib.pod_conv3x3_tc_debug_fault.argtypes = [C.c_int]
+    lib.pod_absmax_accumulate.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.pod_pow2_scale_from_absmax.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    lib.pod_nchw_to_nhwc_split_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pod_conv3x3_simt.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                      C.c_int, C.POINTER(Dropout), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     lib.pod_sample_mean_q1.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]

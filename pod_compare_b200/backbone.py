@@ -12,7 +12,12 @@ architecture with stock torch ops in fp32 (library convolutions, no hand-written
     backbone.top_block.p6/p7.{weight,bias}                  LastLevelP6P7 on res5 (detectron2 v0.2-v0.3)
 
 Preprocessing follows detectron2's `preprocess_image`: (image - PIXEL_MEAN) / PIXEL_STD in the input
-channel order (BGR for the MSRA weights), zero-padded to a multiple of 128.
+channel order (BGR for the MSRA weights), zero-padded (bottom / right) to a multiple of the backbone's
+`size_divisibility`.  For detectron2's FPN that is the stride of the LAST BOTTOM-UP level fed to the FPN
+(res5: 32), not of the top block's P7: a 1280x720 frame becomes 1280x736 (P3 92x160, P4 46x80, P5 23x40, and the
+stride-2 3x3 convolutions give P6 12x20, P7 6x10).  SURVEY 8(d) / BASELINE.md quote the benchmark geometry on a
+128-padded frame (768x1280, P3 96x160); `synthetic.level_shapes` keeps that for the features-in benchmark,
+the head path itself is shape-generic.
 """
 import torch
 import torch.nn.functional as F
@@ -83,7 +88,7 @@ class ResNetFPNBackbone:
     """Callable: list of (3,H,W) images (uint8 or float, one size) -> [P3..P7], each (B,256,Hl,Wl) fp32."""
 
     def __init__(self, state_dict, pixel_mean=(103.530, 116.280, 123.675), pixel_std=(1.0, 1.0, 1.0), device="cuda",
-                 stride_in_1x1=True, size_divisibility=128, eps=1e-5):
+                 stride_in_1x1=True, size_divisibility=32, eps=1e-5):
         self.device = torch.device(device)
         self.stride_in_1x1 = stride_in_1x1
         self.div = size_divisibility

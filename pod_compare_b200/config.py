@@ -124,7 +124,48 @@ def _construct_eval(loader, node):
     args = loader.construct_sequence(node, deep=True)
     if len(args) != 1 or not isinstance(args[0], str):
         raise yaml.YAMLError("unsupported eval payload in config")
-    return eval(args[0], {"__builtins__": {}}, {})  # arithmetic list comprehension only
+    return _safe_arith_eval(args[0])
+
+
+_ARITH_BIN = {ast.Add: lambda a, b: a + b, ast.Sub: lambda a, b: a - b, ast.Mult: lambda a, b: a * b,
+              ast.Div: lambda a, b: a / b, ast.Pow: lambda a, b: a ** b, ast.FloorDiv: lambda a, b: a // b}
+
+
+def _safe_arith_eval(src):
+    """Evaluates the ONE construct the reference's YAML uses -- (nested) list displays / list comprehensions over
+    literal lists whose elements are +,-,*,/,//,** arithmetic on numbers and the comprehension variables -- by walking
+    the AST with a whitelist.  No names other than comprehension targets, no calls, attributes or subscripts: a
+    config file shipped next to a model cannot execute code (python's eval() with emptied builtins can be escaped)."""
+    tree = ast.parse(src, mode="eval")
+
+    def ev(n, env):
+        if isinstance(n, ast.Constant) and isinstance(n.value, (int, float)) and not isinstance(n.value, bool):
+            return n.value
+        if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load) and n.id in env:
+            return env[n.id]
+        if isinstance(n, ast.BinOp) and type(n.op) in _ARITH_BIN:
+            a, b = ev(n.left, env), ev(n.right, env)
+            if isinstance(n.op, ast.Pow) and abs(b) > 64:
+                raise yaml.YAMLError("exponent too large in config expression")
+            return _ARITH_BIN[type(n.op)](a, b)
+        if isinstance(n, ast.UnaryOp) and isinstance(n.op, (ast.USub, ast.UAdd)):
+            v = ev(n.operand, env)
+            return -v if isinstance(n.op, ast.USub) else v
+        if isinstance(n, (ast.List, ast.Tuple)):
+            if len(n.elts) > 4096:
+                raise yaml.YAMLError("list too long in config expression")
+            return [ev(e, env) for e in n.elts]
+        if isinstance(n, ast.ListComp) and len(n.generators) == 1:
+            g = n.generators[0]
+            if g.ifs or g.is_async or not isinstance(g.target, ast.Name):
+                raise yaml.YAMLError("unsupported comprehension in config expression")
+            seq = ev(g.iter, env)
+            if not isinstance(seq, list):
+                raise yaml.YAMLError("comprehension must iterate over a list literal")
+            return [ev(n.elt, dict(env, **{g.target.id: x})) for x in seq]
+        raise yaml.YAMLError("unsupported syntax in config expression: %s" % type(n).__name__)
+
+    return ev(tree.body, {})
 
 
 _Loader.add_constructor("tag:yaml.org,2002:python/object/apply:eval", _construct_eval)

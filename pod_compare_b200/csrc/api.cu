@@ -14,6 +14,18 @@ void pod_set_error(const char* fmt, ...) {
 extern "C" __attribute__((visibility("default"))) const char* pod_last_error(void) { return g_err; }
 extern "C" __attribute__((visibility("default"))) int pod_version(void) { return POD_ABI_VERSION; }
 
+// Combined device-side error word of the library (synchronises the device): the product path calls it once per
+// inference call and raises -- a bounded barrier wait that expired or an activation outside the fp16 split range
+// must never come back as a plausible-looking result.
+extern "C" __attribute__((visibility("default"))) int pod_status(int* status_host) {
+  POD_REQUIRE(status_host, "pod_status: null");
+  int a = 0, b = 0, rc;
+  if ((rc = pod_tc_status_fetch(&a))) return rc;
+  if ((rc = pod_prep_status_fetch(&b))) return rc;
+  *status_host = a != 0 ? a : b;
+  return 0;
+}
+
 extern "C" __attribute__((visibility("default"))) int pod_device_ok(void) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;

@@ -12,6 +12,9 @@
 // error plumbing: thread-local message, int return codes (no exceptions cross the ABI)
 // ---------------------------------------------------------------------------------------------
 void pod_set_error(const char* fmt, ...);
+// device-side error words of the kernel files (each reads and clears its own); combined by pod_status (api.cu)
+int pod_tc_status_fetch(int* v);
+int pod_prep_status_fetch(int* v);
 
 #define POD_REQUIRE(cond, ...)                                   \
   do {                                                           \

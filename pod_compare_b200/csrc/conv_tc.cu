@@ -41,7 +41,10 @@ constexpr int NUM_THREADS = 384;         // warpgroup 0: TMA producer (warp 0), 
                                          // warpgroup 0 to the epilogue warps so their 128 running sums stay in registers
 constexpr long long WAIT_LIMIT_CYCLES = 4000000000LL;   // ~2 s: bounded waits, never hang the box
 
-__device__ int g_status = 0;            // 0 ok; else code of the barrier wait that expired
+__device__ int g_status = 0;            // 0 ok; 1..99 = code of the barrier wait that expired; 100 = a hidden activation
+                                        // left the fp16 split range (|x * out_scale| > 65504, would become inf / NaN)
+__device__ long long g_wait_limit = WAIT_LIMIT_CYCLES;   // pod_conv3x3_tc_set_wait_limit (tests shorten it)
+constexpr int STATUS_SATURATED = 100;
 
 struct Params {
   CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
@@ -51,6 +54,8 @@ struct Params {
   int Cout, Cout_pad;
   int relu;
   int dbg_skip_ld;      // debug: skip the TMEM drains (results invalid) to attribute chunk overhead
+  int dbg_fault;        // fault injection (tests): CTA 0's producer never issues its first load -> bounded waits expire
+  const float* in_scale_dev;   // optional device-resident input scale (overrides the host value folded into acc_scale)
   int kb_per_chunk;     // K-blocks summed in the tensor core before an fp32 RN add in registers
   float acc_scale;      // 1 / (in_scale * w_scale)
   float out_scale;
@@ -102,8 +107,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int code) {
   if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
+  const long long limit = g_wait_limit;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > WAIT_LIMIT_CYCLES) {
+    if (clock64() - t0 > limit) {
       atomicCAS(&g_status, 0, code);
       return false;
     }
@@ -293,13 +299,17 @@ __device__ __forceinline__ void dropout_bits_slice(const Params& P, int n, int p
 template <int MODE, int NG>
 __device__ __forceinline__ void tile_epilogue(const Params& P, const float (&sum)[NG * 16], int n, int pixel, int col0,
                                               const uint32_t (&keep)[(NG * 16 + 31) / 32]) {
+    // a device-resident input scale (power of two, written by pod_feature_scale) divides exactly
+    const float acc_scale = P.in_scale_dev != nullptr ? P.acc_scale / __ldg(P.in_scale_dev) : P.acc_scale;
+    const float sat_limit = 65504.f / P.out_scale;
+    bool saturated = false;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       const int ch = col0 + g * 16;
       float v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        v[i] = fmaf(sum[g * 16 + i], P.acc_scale, __ldg(P.bias + ch + i));
+        v[i] = fmaf(sum[g * 16 + i], acc_scale, __ldg(P.bias + ch + i));
         if (P.relu) v[i] = fmaxf(v[i], 0.f);
       }
       if (MODE == POD_OUT_HIDDEN) {
@@ -308,6 +318,10 @@ __device__ __forceinline__ void tile_epilogue(const Params& P, const float (&sum
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = ((bits >> i) & 1u) ? v[i] * P.drop_scale : 0.f;
         }
+        // the fp16 split pair holds |x * out_scale| <= 65504; beyond it hi becomes inf and every later layer NaN.
+        // The reference computes in fp32 and has no such limit, so this is reported, never silent (also catches NaN).
+#pragma unroll
+        for (int i = 0; i < 16; ++i) saturated |= !(fabsf(v[i]) <= sat_limit);
         uint32_t ph[8], pl[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -344,6 +358,7 @@ __device__ __forceinline__ void tile_epilogue(const Params& P, const float (&sum
         }
       }
     }
+    if (MODE == POD_OUT_HIDDEN && saturated) atomicCAS(&g_status, 0, STATUS_SATURATED);
 }
 
 template <int BN, int BK, int MODE, bool HALO>
@@ -416,7 +431,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
     if (warp == 0 && lane == 0) {
       // ================================ TMA producer ================================
       uint32_t stage = 0, phase = 0;
-      bool ok = true;
+      bool ok = !(P.dbg_fault && blockIdx.x == 0);     // fault injection: CTA 0 never loads -> its waits expire
       if constexpr (HALO) {
         uint32_t as = 0, aphase = 0;
         for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
@@ -779,7 +794,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
     // ================================ TMA producer (both CTAs) ================================
     uint32_t stage = 0, phase = 0;
     [[maybe_unused]] uint32_t as = 0, aphase = 0;
-    bool ok = true;
+    bool ok = !(P.dbg_fault && pair0 == 0);            // fault injection: pair 0 never loads -> its waits expire
     for (int tp = pair0; tp < num_pairs && ok; tp += pair_step) {
       const int tile = 2 * tp + (int)rank;
       // the odd tail tile of the last pair loads map index NB: entirely out of bounds -> zero fill
@@ -1129,7 +1144,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_wt(const __grid_cons
     if (warp == 0 && lane == 0) {
       // ================================ TMA producer ================================
       uint32_t xs = 0, xphase = 0, ws = 0, wphase = 0;
-      bool ok = true;
+      bool ok = !(P.dbg_fault && blockIdx.x == 0);     // fault injection: CTA 0 never loads -> its waits expire
       for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
         const int n = physical_map(P, tile / tiles_per_map), r = tile % tiles_per_map;
         const int y0 = (r / P.tiles_x) * WT_TILE, x0 = (r % P.tiles_x) * WT_TILE;
@@ -1354,6 +1369,19 @@ static int g_tc_chunk_kb = 12; // if > 0: K-blocks per accumulation chunk (must 
                                // default 12 x 64 channels = 3 taps: 3 TMEM drains per tile; with the truncation compensation
                                // this is more accurate than 6-K-block chunks without it and 10 % faster
 
+static int g_tc_fault = 0;    // pod_conv3x3_tc_debug_fault
+
+extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_wait_limit(long long cycles) {
+  if (cycles <= 0) cycles = tc::WAIT_LIMIT_CYCLES;
+  POD_CUDA(cudaMemcpyToSymbol(tc::g_wait_limit, &cycles, sizeof(cycles)));
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_debug_fault(int on) {
+  g_tc_fault = on ? 1 : 0;
+  return 0;
+}
+
 extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_chunk_kblocks(int kb) {
   POD_REQUIRE(kb >= 0, "pod_conv3x3_tc_set_chunk_kblocks: must be >= 0");
   g_tc_chunk_kb = kb;
@@ -1411,12 +1439,13 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
               "pod_conv3x3_tc: in_map_stride too small or not 16-byte aligned");
   POD_REQUIRE(((uintptr_t)a->in_hi | (uintptr_t)a->in_lo | (uintptr_t)a->w_hi | (uintptr_t)a->w_lo) % 16 == 0,
               "pod_conv3x3_tc: operands must be 16-byte aligned");
-  POD_REQUIRE(a->in_scale > 0.f && a->w_scale > 0.f, "pod_conv3x3_tc: scales must be positive");
+  POD_REQUIRE((a->in_scale > 0.f || a->in_scale_dev) && a->w_scale > 0.f, "pod_conv3x3_tc: scales must be positive");
   Params P;
   memset(&P, 0, sizeof(P));
   const int BK = g_tc_bk;
   // weights-as-A: RAW mode, <= 64 output channels, single destination, hi|lo weight halves adjacent (stacked along M)
   const bool wt = g_tc_wt && BK == 64 && a->mode == POD_OUT_RAW && a->Cout_pad == 64 && a->out2_f32 == nullptr &&
+                  a->in_scale_dev == nullptr &&
                   (const char*)a->w_lo == (const char*)a->w_hi + (size_t)64 * 9 * a->Cin * 2;
   if (wt) {
     POD_REQUIRE(a->out_f32 && a->out_pixel_stride >= a->Cout, "pod_conv3x3_tc: raw mode needs out_f32 / pixel stride >= Cout");
@@ -1450,6 +1479,7 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
     P.bias = a->bias;
     P.out_f32 = a->out_f32;
     P.out_map_stride = a->out_map_stride; P.out_pixel_stride = a->out_pixel_stride;
+    P.dbg_fault = g_tc_fault;
     return wt_halo ? launch_wt<true>(P, (cudaStream_t)stream) : launch_wt<false>(P, (cudaStream_t)stream);
   }
   const bool halo = (g_tc_halo & 1) && BK == 64;
@@ -1481,7 +1511,10 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   P.kb_per_chunk = g_tc_taps * (a->Cin / BK);
   if (g_tc_chunk_kb > 0 && (9 * (a->Cin / BK)) % g_tc_chunk_kb == 0) P.kb_per_chunk = g_tc_chunk_kb;
   P.dbg_skip_ld = getenv("POD_TC_DEBUG_SKIP_LD") ? 1 : 0;
-  P.acc_scale = 1.0f / (a->in_scale * a->w_scale) * trunc_comp_factor(P.kb_per_chunk, BK, a->Cout_pad <= 128 ? 2 : 3);
+  P.dbg_fault = g_tc_fault;
+  P.in_scale_dev = a->in_scale_dev;
+  P.acc_scale = 1.0f / ((a->in_scale_dev ? 1.0f : a->in_scale) * a->w_scale) *
+                trunc_comp_factor(P.kb_per_chunk, BK, a->Cout_pad <= 128 ? 2 : 3);
   P.out_scale = a->out_scale;
   P.bias = a->bias;
   P.out_hi = (__half*)a->out_hi; P.out_lo = (__half*)a->out_lo; P.out_f32 = a->out_f32;
@@ -1528,14 +1561,17 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   return a->mode == POD_OUT_HIDDEN ? dispatch_bn<32, POD_OUT_HIDDEN, false>(P, st) : dispatch_bn<32, POD_OUT_RAW, false>(P, st);
 }
 
-extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_status(int* status_host) {
-  POD_REQUIRE(status_host, "pod_conv3x3_tc_status: null");
-  int v = 0;
-  POD_CUDA(cudaMemcpyFromSymbol(&v, tc::g_status, sizeof(int)));
-  *status_host = v;
-  if (v != 0) {
+int pod_tc_status_fetch(int* v) {
+  *v = 0;
+  POD_CUDA(cudaMemcpyFromSymbol(v, tc::g_status, sizeof(int)));
+  if (*v != 0) {
     int zero = 0;
     POD_CUDA(cudaMemcpyToSymbol(tc::g_status, &zero, sizeof(int)));
   }
   return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_status(int* status_host) {
+  POD_REQUIRE(status_host, "pod_conv3x3_tc_status: null");
+  return pod_tc_status_fetch(status_host);
 }

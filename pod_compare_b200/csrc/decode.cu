@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) k_decode(pod_decode_args a, SegTable st, 
           d[i] = __fadd_rn(md[i], acc);
         }
       }
-      decode_box(d, A, a.wx, a.wy, a.ww, a.wh, clampv, x);
+      decode_box(d, A, a.swx, a.swy, a.sww, a.swh, clampv, x);      // SampleBox2BoxTransform weights (RPN)
     };
     mean_cov(a.box_draws, lane, ref, gen, box, cov);
   }
@@ -195,6 +195,11 @@ extern "C" __attribute__((visibility("default"))) int pod_decode_cov(const pod_d
   POD_REQUIRE(!a->mean_regvar || a->box_draws > 1, "pod_decode_cov: box_draws must be > 1");
   POD_REQUIRE(a->runs >= 1, "pod_decode_cov: runs must be >= 1");
   POD_REQUIRE(a->wx > 0 && a->wy > 0 && a->ww > 0 && a->wh > 0, "pod_decode_cov: regression weights must be positive");
+  pod_decode_args args = *a;
+  if (args.swx == 0.f && args.swy == 0.f && args.sww == 0.f && args.swh == 0.f) {
+    args.swx = a->wx; args.swy = a->wy; args.sww = a->ww; args.swh = a->wh;
+  }
+  POD_REQUIRE(args.swx > 0 && args.swy > 0 && args.sww > 0 && args.swh > 0, "pod_decode_cov: sampled-decode weights must be positive");
   SegTable st;
   st.n_levels = a->n_levels;
   for (int l = 0; l <= a->n_levels; ++l) st.seg[l] = a->seg_off_host[l];
@@ -203,7 +208,7 @@ extern "C" __attribute__((visibility("default"))) int pod_decode_cov(const pod_d
   const int64_t blocks = (warps * 32 + 255) / 256;
   POD_REQUIRE(blocks < (1ll << 31), "pod_decode_cov: launch too large");
   const float clampv = (float)log(1000.0 / 16.0);
-  k_decode<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*a, st, pod_key(a->seed, POD_STREAM_BOX), clampv);
+  k_decode<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(args, st, pod_key(a->seed, POD_STREAM_BOX), clampv);
   POD_LAUNCH_CHECK();
   return 0;
 }

@@ -1,13 +1,83 @@
 // Operand preparation and streaming statistics kernels (HBM-bound elementwise / transpose work).
 #include "common.cuh"
 
+// Device-side error word of this file's kernels (read and cleared by pod_status):
+//   101 = a first-layer activation left the fp16 split range in k_mask_expand, 102 = non-finite input feature.
+__device__ int g_prep_status = 0;
+
+int pod_prep_status_fetch(int* v) {
+  *v = 0;
+  POD_CUDA(cudaMemcpyFromSymbol(v, g_prep_status, sizeof(int)));
+  if (*v != 0) {
+    int zero = 0;
+    POD_CUDA(cudaMemcpyToSymbol(g_prep_status, &zero, sizeof(int)));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp16 split scale of the input feature maps, computed on the device (no host round trip):
+//   k_absmax accumulates max|x| of one tensor into a word (bit pattern of a non-negative float orders like uint),
+//   k_pow2_scale turns it into  min(max_scale, largest power of two s with amax * s <= target).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_absmax(const float* __restrict__ x, int64_t n, uint32_t* __restrict__ amax_bits) {
+  float m = 0.f;
+  bool bad = false;
+  const int64_t n4 = n / 4;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + t);
+    const float a = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    bad |= !(fabsf(v.x) <= 3.0e38f) | !(fabsf(v.y) <= 3.0e38f) | !(fabsf(v.z) <= 3.0e38f) | !(fabsf(v.w) <= 3.0e38f);
+    m = fmaxf(m, a);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int64_t t = n4 * 4; t < n; ++t) {
+      bad |= !(fabsf(x[t]) <= 3.0e38f);
+      m = fmaxf(m, fabsf(x[t]));
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
+  if (bad) atomicCAS(&g_prep_status, 0, 102);
+}
+
+__global__ void k_pow2_scale(const uint32_t* __restrict__ amax_bits, float max_scale, float target, float* __restrict__ scale) {
+  const float amax = __uint_as_float(*amax_bits);
+  float s = max_scale;
+  if (amax > 0.f && amax <= 3.0e38f) {
+    int e, et;
+    const float m = frexpf(amax, &e);        // amax = m * 2^e, m in [0.5, 1)
+    (void)frexpf(target, &et);               // target = 2^(et-1) (power of two)
+    const float p = ldexpf(1.f, (et - 1) - e + (m == 0.5f ? 1 : 0));
+    s = fminf(max_scale, p);
+  }
+  *scale = s;
+}
+
+extern "C" __attribute__((visibility("default"))) int pod_absmax_accumulate(const float* x, int64_t n, uint32_t* amax_bits, void* stream) {
+  POD_REQUIRE(x && amax_bits && n > 0 && (uintptr_t)x % 16 == 0, "pod_absmax_accumulate: bad args (16-byte aligned input)");
+  const int64_t want = (n / 4 + 255) / 256 + 1, cap = (int64_t)pod_num_sms() * 8;
+  k_absmax<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(x, n, amax_bits);
+  POD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pod_pow2_scale_from_absmax(const uint32_t* amax_bits, float max_scale, float target, float* scale_dev,
+                                                                   void* stream) {
+  POD_REQUIRE(amax_bits && scale_dev && max_scale > 0.f && target > 0.f, "pod_pow2_scale_from_absmax: bad args");
+  k_pow2_scale<<<1, 1, 0, (cudaStream_t)stream>>>(amax_bits, max_scale, target, scale_dev);
+  POD_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // NCHW fp32 -> NHWC (fp16 split pair | fp32): 32x32 shared-memory transpose tiles
 // ---------------------------------------------------------------------------------------------
 template <bool SPLIT>
-__global__ void k_nchw_to_nhwc(const float* __restrict__ src, int C, int HW, float scale, __half* __restrict__ hi,
-                               __half* __restrict__ lo, float* __restrict__ dst32) {
+__global__ void k_nchw_to_nhwc(const float* __restrict__ src, int C, int HW, float scale, const float* __restrict__ scale_dev,
+                               __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ dst32) {
   __shared__ float tile[32][33];
+  if (SPLIT && scale_dev != nullptr) scale = __ldg(scale_dev);
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const float* s = src + (int64_t)n * C * HW;
@@ -38,7 +108,19 @@ extern "C" __attribute__((visibility("default"))) int pod_nchw_to_nhwc_split(con
   POD_REQUIRE(src && dst_hi && dst_lo && NB > 0 && C > 0 && H > 0 && W > 0, "pod_nchw_to_nhwc_split: bad args");
   POD_REQUIRE(NB <= 65535, "pod_nchw_to_nhwc_split: NB too large for one launch");
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, NB), block(32, 8);
-  k_nchw_to_nhwc<true><<<grid, block, 0, (cudaStream_t)stream>>>(src, C, H * W, scale, (__half*)dst_hi, (__half*)dst_lo,
+  k_nchw_to_nhwc<true><<<grid, block, 0, (cudaStream_t)stream>>>(src, C, H * W, scale, nullptr, (__half*)dst_hi, (__half*)dst_lo,
+                                                                 nullptr);
+  POD_LAUNCH_CHECK();
+  return 0;
+}
+
+// same, with the scale read from device memory (pod_pow2_scale_from_absmax): no host synchronisation
+extern "C" __attribute__((visibility("default"))) int pod_nchw_to_nhwc_split_dev(const float* src, int NB, int C, int H, int W, const float* scale_dev,
+                                          void* dst_hi, void* dst_lo, void* stream) {
+  POD_REQUIRE(src && scale_dev && dst_hi && dst_lo && NB > 0 && C > 0 && H > 0 && W > 0, "pod_nchw_to_nhwc_split_dev: bad args");
+  POD_REQUIRE(NB <= 65535, "pod_nchw_to_nhwc_split_dev: NB too large for one launch");
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, NB), block(32, 8);
+  k_nchw_to_nhwc<true><<<grid, block, 0, (cudaStream_t)stream>>>(src, C, H * W, 1.f, scale_dev, (__half*)dst_hi, (__half*)dst_lo,
                                                                  nullptr);
   POD_LAUNCH_CHECK();
   return 0;
@@ -47,7 +129,7 @@ extern "C" __attribute__((visibility("default"))) int pod_nchw_to_nhwc_split(con
 extern "C" __attribute__((visibility("default"))) int pod_nchw_to_nhwc_f32(const float* src, int NB, int C, int H, int W, float* dst, void* stream) {
   POD_REQUIRE(src && dst && NB > 0 && NB <= 65535 && C > 0 && H > 0 && W > 0, "pod_nchw_to_nhwc_f32: bad args");
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, NB), block(32, 8);
-  k_nchw_to_nhwc<false><<<grid, block, 0, (cudaStream_t)stream>>>(src, C, H * W, 1.f, nullptr, nullptr, dst);
+  k_nchw_to_nhwc<false><<<grid, block, 0, (cudaStream_t)stream>>>(src, C, H * W, 1.f, nullptr, nullptr, nullptr, dst);
   POD_LAUNCH_CHECK();
   return 0;
 }
@@ -113,6 +195,10 @@ k_mask_expand(const float* __restrict__ x, int64_t oct_per_map, int NB_in, pod_d
     const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
     // the kept value (and its fp16 split) does not depend on the sample: split once, select per copy
     uint32_t kh[4], kl[4];
+    bool saturated = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) saturated |= !(fabsf(v[i] * dscale * scale) <= 65504.f);
+    if (saturated) atomicCAS(&g_prep_status, 0, 101);    // fp16 split range exceeded (or NaN): reported, never silent
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       __half h0, l0, h1, l1;

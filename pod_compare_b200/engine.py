@@ -116,7 +116,8 @@ class PathConfig:
     score_thresh: float = 0.05
     nms_thresh: float = 0.5
     max_dets: int = 100
-    reg_weights: tuple = (1.0, 1.0, 1.0, 1.0)
+    reg_weights: tuple = (1.0, 1.0, 1.0, 1.0)           # MODEL.RETINANET.BBOX_REG_WEIGHTS (apply_deltas)
+    sample_reg_weights: tuple = None                    # MODEL.RPN.BBOX_REG_WEIGHTS (sampled decode); None = same
     affinity: float = 0.9
     box_merge: str = "bayesian_inference"
     cls_merge: str = "max_score"
@@ -143,16 +144,15 @@ class HeadEngine:
     @staticmethod
     def feature_scale(feats):
         """fp16 split scale of the input maps: ACT_SCALE unless a feature exceeds its range (|x|*scale must stay
-        below fp16's 65504), in which case the largest smaller power of two.  One device reduction + sync."""
-        amax = float(torch.stack([f.abs().amax() for f in feats]).max())
-        if not math.isfinite(amax):
-            raise PodError("non-finite values in the input feature maps")
-        return min(ACT_SCALE, ops.pow2_scale(amax, 32768.0)) if amax > 0 else ACT_SCALE
+        below fp16's 65504), in which case the largest smaller power of two.  Computed by two small kernels into a
+        device word that the layout kernel and the first tower convolution read: no torch ops, no host sync
+        (non-finite inputs raise through ops.check_status at the end of the call)."""
+        return ops.feature_scale_dev(feats, ACT_SCALE, 32768.0)
 
-    def _conv_hidden(self, src, NB, H, W, pcv, dst, drop, in_scale=ACT_SCALE, map_group=0, map_live=0):
+    def _conv_hidden(self, src, NB, H, W, pcv, dst, drop, in_scale=ACT_SCALE, map_group=0, map_live=0, in_scale_dev=None):
         ops.conv3x3_tc(src[0], src[1], in_scale, NB, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, pcv.cout,
                        pcv.cout_pad, POD_OUT_HIDDEN, True, out_hi=dst[0], out_lo=dst[1], out_scale=ACT_SCALE, drop=drop,
-                       map_group=map_group, map_live=map_live)
+                       map_group=map_group, map_live=map_live, in_scale_dev=in_scale_dev)
 
     def _conv_out(self, src, NB, H, W, blocks, out, out_offset, out_map_stride, in_map_stride=None, in_offset=0,
                   map_group=0, map_live=0):
@@ -196,15 +196,16 @@ class HeadEngine:
         for lvl, f in enumerate(feats):
             H, W = level_hw[lvl]
             HW = H * W
-            fhi, flo = ops.nchw_to_nhwc_split(f.contiguous(), fscale)
+            fhi, flo = ops.nchw_to_nhwc_split_dev(f.contiguous(), fscale)
             for tower in (TOWER_CLS, TOWER_BOX):
                 tw = w.towers[tower]
                 has_var = pc.cls_var if tower == TOWER_CLS else pc.bbox_cov
                 t_passes = 2 if has_var else 1
                 # layer 0: conv + ReLU once per image, then N x passes masked copies (Q2 hoist)
                 p0 = tw[0]
-                ops.conv3x3_tc(fhi, flo, fscale, B, H, W, 256, p0.w_hi, p0.w_lo, p0.w_scale, p0.bias, 256, 256,
-                               POD_OUT_RAW, True, out_f32=c1, out_map_stride=HW * 256, out_pixel_stride=256)
+                ops.conv3x3_tc(fhi, flo, 1.0, B, H, W, 256, p0.w_hi, p0.w_lo, p0.w_scale, p0.bias, 256, 256,
+                               POD_OUT_RAW, True, out_f32=c1, out_map_stride=HW * 256, out_pixel_stride=256,
+                               in_scale_dev=fscale)
                 d0 = ops.make_dropout(pc.dropout_rate, seed, image0, n_mc, t_passes, 0, tower, 0, lvl)
                 # maps of one image: sample-major, pass-minor; the unread ones (skip_unread) are its tail
                 grp = n_mc * t_passes
@@ -233,18 +234,28 @@ class HeadEngine:
                                    in_map_stride=2 * HW * 256, in_offset=HW * 256, map_group=n_mc, map_live=n_live)
         return raw, level_off
 
-    def head_eval(self, feats, members=None, skip_unread=False):
+    def head_eval(self, feats, members=None, skip_unread=False, per_member_feats=False):
         """Deterministic head (eval mode): one forward per weight set; the reference's second tower
         evaluation is identical to the first and is shared.  Returns (B, E, R, D) raw outputs.
+        per_member_feats: feats[e][l] -- every ensemble member reads its OWN feature maps (each member of the
+        reference is a full model with its own backbone, probabilistic_inference.py:58-77,499-501); otherwise one
+        list over levels shared by all members.
         skip_unread (see head_mc): the class tower of the LAST member feeds only outputs the Q1 mean never reads
         and is not evaluated; rows [:, E-1] of logits / logvar stay unwritten (regvar is written: it shares the
         fused box convolution with the deltas)."""
         pc = self.pc
         members = members if members is not None else list(range(len(self.ws)))
         E = len(members)
+        feat_sets = list(feats) if per_member_feats else [feats]
+        if per_member_feats and len(feat_sets) != E:
+            raise PodError("head_eval: %d feature sets for %d members" % (len(feat_sets), E))
+        feats = feat_sets[0]
         B = feats[0].shape[0]
         A, K = pc.num_anchors, pc.num_classes
         level_hw = [tuple(f.shape[-2:]) for f in feats]
+        for fs in feat_sets[1:]:
+            if [tuple(f.shape) for f in fs] != [tuple(f.shape) for f in feats]:
+                raise PodError("head_eval: every member's feature maps must have the same shapes")
         level_off = [0]
         for (h, wd) in level_hw:
             level_off.append(level_off[-1] + h * wd * A)
@@ -257,19 +268,20 @@ class HeadEngine:
         max_hw = max(h * wd for h, wd in level_hw)
         act = [(self._get("a%d_hi" % i, B * max_hw * 256, torch.float16),
                 self._get("a%d_lo" % i, B * max_hw * 256, torch.float16)) for i in range(2)]
-        fscale = self.feature_scale(feats)
-        for lvl, f in enumerate(feats):
+        fscales = [self.feature_scale(fs) for fs in feat_sets]
+        for lvl in range(len(feats)):
             H, W = level_hw[lvl]
-            fhi, flo = ops.nchw_to_nhwc_split(f.contiguous(), fscale)
+            split_maps = [ops.nchw_to_nhwc_split_dev(fs[lvl].contiguous(), sc) for fs, sc in zip(feat_sets, fscales)]
             for e, mi in enumerate(members):
                 w = self.ws[mi]
+                (fhi, flo), fscale = split_maps[e if per_member_feats else 0], fscales[e if per_member_feats else 0]
                 for tower in (TOWER_CLS, TOWER_BOX):
                     if skip_unread and E > 1 and e == E - 1 and tower == TOWER_CLS:
                         continue
                     tw = w.towers[tower]
                     src, cur = (fhi, flo), 0
                     for layer in range(len(tw)):
-                        self._conv_hidden(src, B, H, W, tw[layer], act[cur], None, in_scale=fscale if layer == 0 else ACT_SCALE)
+                        self._conv_hidden(src, B, H, W, tw[layer], act[cur], None, in_scale_dev=fscale if layer == 0 else None)
                         src = act[cur]
                         cur ^= 1
                     mean_pc, var_pc = (w.cls_score, w.cls_var) if tower == TOWER_CLS else (w.bbox_pred, w.bbox_cov)
@@ -320,7 +332,8 @@ class HeadEngine:
         probs, score, cls = ops.scores(m_logits, m_logvar, level_off, pc.cls_var_num_samples, seed, image0, runs=runs)
         cand_idx, cand_cnt, seg = ops.topk_levels(score, level_off, pc.topk, pc.score_thresh)
         cand = ops.decode_cov(m_deltas, m_regvar, raw["deltas"] if S > 1 else None, anchors, probs, score, cls,
-                              cand_idx, cand_cnt, seg, pc.box_num_samples, seed, image0, pc.reg_weights, runs=runs)
+                              cand_idx, cand_cnt, seg, pc.box_num_samples, seed, image0, pc.reg_weights, runs=runs,
+                              sample_reg_weights=pc.sample_reg_weights)
         return cand
 
     def detections(self, cand, fuse_mode, image_hw, out_hw, nms_variant=ops.NMS_AUTO, skip_post=False):

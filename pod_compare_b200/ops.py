@@ -85,6 +85,35 @@ def nchw_to_nhwc_split(x, scale):
     return hi, lo
 
 
+def feature_scale_dev(feats, max_scale, target=32768.0):
+    """fp16 split scale of the input maps, computed on the device: min(max_scale, largest power of two s with
+    max|x| * s <= target).  Returns a 1-element fp32 CUDA tensor (no host synchronisation); non-finite inputs set
+    the library status word (check_status raises)."""
+    lib = _cabi.require_device()
+    amax = torch.zeros((1,), dtype=torch.int32, device=feats[0].device)
+    scale = torch.empty((1,), dtype=torch.float32, device=feats[0].device)
+    for f in feats:
+        _chk(f, torch.float32, "feature map")
+        check(lib.pod_absmax_accumulate(ptr(f), f.numel(), ptr(amax), stream_ptr()), "pod_absmax_accumulate")
+    check(lib.pod_pow2_scale_from_absmax(ptr(amax), float(max_scale), float(target), ptr(scale), stream_ptr()),
+          "pod_pow2_scale_from_absmax")
+    _count(len(feats) + 1)
+    return scale
+
+
+def nchw_to_nhwc_split_dev(x, scale_dev):
+    lib = _cabi.require_device()
+    _chk(x, torch.float32, "x")
+    _chk(scale_dev, torch.float32, "scale_dev")
+    NB, Cn, H, W = x.shape
+    hi = torch.empty((NB, H, W, Cn), dtype=torch.float16, device=x.device)
+    lo = torch.empty_like(hi)
+    check(lib.pod_nchw_to_nhwc_split_dev(ptr(x), NB, Cn, H, W, ptr(scale_dev), ptr(hi), ptr(lo), stream_ptr()),
+          "pod_nchw_to_nhwc_split_dev")
+    _count()
+    return hi, lo
+
+
 def nchw_to_nhwc_f32(x):
     lib = _cabi.require_device()
     _chk(x, torch.float32, "x")
@@ -144,9 +173,9 @@ def mask_expand_split(x, drop, scale, out_hi=None, out_lo=None, live_reps=0):
 def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias, Cout, Cout_pad, mode, relu,
                out_hi=None, out_lo=None, out_scale=1.0, out_f32=None, out_map_stride=0, out_pixel_stride=0,
                drop=None, in_map_stride=None, in_offset=0, out_offset=0, out2_f32=None, out2_offset=0, split_col=0,
-               out2_map_stride=0, out2_pixel_stride=0, map_group=0, map_live=0):
+               out2_map_stride=0, out2_pixel_stride=0, map_group=0, map_live=0, in_scale_dev=None):
     """Raw-pointer launch of the tcgen05 convolution. `in_offset`/`out_offset` are ELEMENT offsets
-    into in_hi/in_lo and out_f32."""
+    into in_hi/in_lo and out_f32.  in_scale_dev: 1-element fp32 CUDA tensor replacing in_scale."""
     lib = _cabi.require_device()
     a = ConvArgs()
     esz = 2
@@ -168,6 +197,7 @@ def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias,
         a.out2_f32 = out2_f32.data_ptr() + out2_offset * 4
         a.split_col, a.out2_map_stride, a.out2_pixel_stride = split_col, out2_map_stride, out2_pixel_stride
     a.map_group, a.map_live = int(map_group), int(map_live)
+    a.in_scale_dev = in_scale_dev.data_ptr() if in_scale_dev is not None else None
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -185,6 +215,38 @@ def conv3x3_tc_status():
     v = C.c_int(0)
     check(lib.pod_conv3x3_tc_status(C.byref(v)), "pod_conv3x3_tc_status")
     return v.value
+
+
+STATUS_TEXT = {100: "a hidden tower activation left the fp16 split range (|x| * 16 > 65504): the checkpoint / input "
+                    "produces activations this path cannot represent",
+               101: "a first-layer tower activation left the fp16 split range (|x| * 16 / (1-p) > 65504)",
+               102: "non-finite values in the input feature maps"}
+
+
+def status():
+    """Device-side error word of the library, read and cleared (synchronises the device)."""
+    lib = _cabi.require_device()
+    v = C.c_int(0)
+    check(lib.pod_status(C.byref(v)), "pod_status")
+    return v.value
+
+
+def check_status():
+    """Raise PodError if any kernel since the last check reported a device-side error (expired bounded barrier
+    wait, activation outside the fp16 split range, non-finite input).  Called once per inference call."""
+    v = status()
+    if v != 0:
+        raise _cabi.PodError("libpodb200 device-side error %d: %s -- the results of this call are invalid"
+                             % (v, STATUS_TEXT.get(v, "a bounded mbarrier wait of the tcgen05 convolution expired "
+                                                      "(wait code %d)" % v)))
+
+
+def set_conv_wait_limit(cycles):
+    check(_cabi.require_device().pod_conv3x3_tc_set_wait_limit(int(cycles)), "pod_conv3x3_tc_set_wait_limit")
+
+
+def set_conv_debug_fault(on):
+    check(_cabi.load_library().pod_conv3x3_tc_debug_fault(int(bool(on))), "pod_conv3x3_tc_debug_fault")
 
 
 def set_conv_kblock(bk):
@@ -289,7 +351,7 @@ def topk_levels(score, level_off, topk, thresh):
 
 
 def decode_cov(mean_delta, mean_regvar, sample_delta, anchors, probs, score, cls, cand_idx, cand_cnt, seg, box_draws,
-               seed, image0, reg_weights, runs=1):
+               seed, image0, reg_weights, runs=1, sample_reg_weights=None):
     lib = _cabi.require_device()
     B, R, K = probs.shape
     cap = seg[-1]
@@ -318,6 +380,7 @@ def decode_cov(mean_delta, mean_regvar, sample_delta, anchors, probs, score, cls
     a.box_draws, a.seed, a.image0 = box_draws, int(seed) & 0xFFFFFFFFFFFFFFFF, image0
     a.runs = runs
     a.wx, a.wy, a.ww, a.wh = [float(v) for v in reg_weights]
+    a.swx, a.swy, a.sww, a.swh = [float(v) for v in (sample_reg_weights or reg_weights)]
     a.out_boxes, a.out_cov = out["boxes"].data_ptr(), out["cov"].data_ptr()
     a.out_scores, a.out_classes = out["scores"].data_ptr(), out["classes"].data_ptr()
     a.out_probs, a.out_count, a.out_anchor = out["probs"].data_ptr(), out["count"].data_ptr(), out["anchor"].data_ptr()

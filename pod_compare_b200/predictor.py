@@ -76,6 +76,7 @@ class ProbabilisticPredictor:
         else:
             self.model.eval()
         self.backbone = None
+        self.member_backbones = None      # ensembles: one backbone per member (load_backbone with E state dicts)
         # Pre-NMS aggregation never reads box_cls / box_cls_var / box_reg_var of the last sample or member
         # (reference probabilistic_inference.py:216-267 loops over range(len-1)): the tower passes feeding
         # only those outputs are left out.  Results are unchanged; set False to evaluate them anyway.
@@ -100,6 +101,10 @@ class ProbabilisticPredictor:
                 sd = torch.load(p, map_location="cpu")
                 sds.append(sd.get("model", sd))
             self.load_weight_sets(sds)
+            # a full-model checkpoint also carries the ResNet-FPN weights (detectron2 key names): with them
+            # build_predictor(cfg)(input_im) works from raw images exactly like the reference's
+            if all(any(k.startswith("backbone.") for k in sd) for sd in sds):
+                self.load_backbone(sds if len(sds) > 1 else sds[0])
 
     # ---------------------------------------------------------------------------------------------
     def path_config(self):
@@ -113,6 +118,8 @@ class ProbabilisticPredictor:
             cov_dims=m.bbox_cov_dims, cls_var_num_samples=m.cls_var_num_samples, box_num_samples=1000,
             topk=m.test_topk_candidates, score_thresh=m.test_score_thresh, nms_thresh=m.test_nms_thresh,
             max_dets=m.max_detections_per_image, reg_weights=tuple(cfg.MODEL.RETINANET.BBOX_REG_WEIGHTS),
+            # the sampled decode uses the RPN weights (reference probabilistic_inference.py:175-176)
+            sample_reg_weights=tuple(cfg.MODEL.RPN.BBOX_REG_WEIGHTS),
             affinity=pi.AFFINITY_THRESHOLD, box_merge=pi.BAYES_OD.BOX_MERGE_MODE, cls_merge=pi.BAYES_OD.CLS_MERGE_MODE)
 
     def load_weight_sets(self, state_dicts):
@@ -125,11 +132,18 @@ class ProbabilisticPredictor:
         self._engine = HeadEngine(self.path_config(), self.weight_sets, self.device)
         return self
 
-    def load_backbone(self, state_dict):
-        """Install the torch ResNet-50-FPN feature extractor (detectron2 key names, backbone.py) so that
-        `predictor(input_im)` accepts raw images."""
+    def load_backbone(self, state_dicts):
+        """Install the ResNet-50-FPN feature extractor (detectron2 key names, backbone.py) so that
+        `predictor(input_im)` accepts raw images.  One state dict, or E of them for INFERENCE_MODE 'ensembles':
+        every ensemble member of the reference is a full model with its own backbone, hence its own feature maps
+        (reference probabilistic_inference.py:58-77,499-501; probabilistic_retinanet.py:99)."""
         from .backbone import ResNetFPNBackbone
-        self.backbone = ResNetFPNBackbone(state_dict, self.cfg.MODEL.PIXEL_MEAN, self.cfg.MODEL.PIXEL_STD, self.device)
+        if isinstance(state_dicts, dict):
+            state_dicts = [state_dicts]
+        nets = [ResNetFPNBackbone(sd, self.cfg.MODEL.PIXEL_MEAN, self.cfg.MODEL.PIXEL_STD, self.device)
+                for sd in state_dicts]
+        self.backbone = nets[0]
+        self.member_backbones = nets if len(nets) > 1 else None
         return self
 
     def _anchors(self, level_hw):
@@ -159,14 +173,23 @@ class ProbabilisticPredictor:
         if len(set(out_hw)) != 1:
             raise ValueError("predict_batch needs one output resolution per batch")
         if all("features" in d for d in dicts):
-            n_lvl = len(dicts[0]["features"])
-            feats = [torch.cat([d["features"][l].reshape((-1,) + tuple(d["features"][l].shape[-3:])) for d in dicts], 0)
-                     for l in range(n_lvl)]
+            def batch_levels(get):
+                n_lvl = len(get(dicts[0]))
+                return [torch.cat([get(d)[l].reshape((-1,) + tuple(get(d)[l].shape[-3:])) for d in dicts], 0)
+                        for l in range(n_lvl)]
+            if isinstance(dicts[0]["features"][0], (list, tuple)):      # ensembles: features[e][l], one set per member
+                feats = [batch_levels(lambda d, e=e: d["features"][e]) for e in range(len(dicts[0]["features"]))]
+            else:
+                feats = batch_levels(lambda d: d["features"])
         else:
             if self.backbone is None:
                 raise _cabi.PodError("no 'features' in the inputs and predictor.backbone is not set "
                                      "(the ResNet-FPN backbone is upstream of this path)")
-            feats = self.backbone([d["image"] for d in dicts])
+            images = [d["image"] for d in dicts]
+            if self.inference_mode == 'ensembles' and self.member_backbones is not None:
+                feats = [net(images) for net in self.member_backbones]   # every member sees its own feature maps
+            else:
+                feats = self.backbone(images)
         ids = [d.get("image_id", i) for i, d in enumerate(dicts)]
         image0 = ids[0] if all(isinstance(i, int) for i in ids) and ids == list(range(ids[0], ids[0] + len(ids))) else 0
         return self.infer_from_features(feats, hw[0], out_hw[0], image0=image0)
@@ -181,11 +204,19 @@ class ProbabilisticPredictor:
         while chunk i computes.  Results are identical to one call per chunk (noise streams are keyed by image id)."""
         if self._engine is None:
             raise _cabi.PodError("no weights loaded: call load_weight_sets(state_dicts) first")
-        B = int(feats[0].shape[0])
+        # ensembles may carry one feature set per member: feats[e][l] (each member of the reference is a full model
+        # with its own backbone, probabilistic_inference.py:499-501); a flat list is shared by all members
+        per_member = isinstance(feats[0], (list, tuple))
+        if per_member and self.inference_mode != 'ensembles':
+            raise ValueError("per-member feature sets are only meaningful for INFERENCE_MODE 'ensembles'")
+        if per_member and len(feats) != len(self.weight_sets):
+            raise _cabi.PodError("got %d feature sets for %d ensemble members" % (len(feats), len(self.weight_sets)))
+        lv0 = feats[0] if per_member else feats
+        B = int(lv0[0].shape[0])
         if chunk_images is None and B > 1:
             # keep the activation working set inside the budget (default 64 GB of the 180 GB): a batch of 64 images at
             # N=30 would otherwise ask for 2 x 64 x 60 maps of 96x160x256 split pairs = 240 GB
-            auto = max(1, int(self.max_activation_bytes // self._activation_bytes_per_image(feats)))
+            auto = max(1, int(self.max_activation_bytes // self._activation_bytes_per_image(lv0)))
             if auto < B and not return_raw:
                 chunk_images = auto
         if chunk_images is not None and 0 < int(chunk_images) < B:
@@ -201,18 +232,24 @@ class ProbabilisticPredictor:
         out_hw = tuple(out_hw) if out_hw is not None else tuple(image_hw)
         seed = self.rng_seed if seed is None else seed
         eng = self._engine
-        feats = [f.to(self.device, dtype=torch.float32, non_blocking=True).contiguous() for f in feats]
-        level_hw = [tuple(f.shape[-2:]) for f in feats]
+        def to_dev(fs):
+            return [f.to(self.device, dtype=torch.float32, non_blocking=True).contiguous() for f in fs]
+        feats = [to_dev(fs) for fs in feats] if per_member else to_dev(feats)
+        level_hw = [tuple(f.shape[-2:]) for f in (feats[0] if per_member else feats)]
         anchors = self._anchors(level_hw)
         if mode == 'ensembles':
             if len(self.weight_sets) != len(pi.ENSEMBLES.RANDOM_SEED_NUMS):
                 raise _cabi.PodError("ensembles mode needs one weight set per RANDOM_SEED_NUMS entry")
-            raw, level_off = eng.head_eval(feats, skip_unread=self.skip_unread_outputs and not post_nms)
+            raw, level_off = eng.head_eval(feats, skip_unread=self.skip_unread_outputs and not post_nms,
+                                           per_member_feats=per_member)
+        elif self.mc_dropout_enabled and self.model.use_dropout:
+            # NUM_RUNS == 1 keeps the reference's behaviour too: the model stays in train mode (:52-56), so the single
+            # forward has active dropout and the mean / variance heads see independently masked tower passes (Q2)
+            n_runs = max(1, int(self.num_mc_dropout_runs))
+            raw, level_off = eng.head_mc(feats, n_runs, seed, image0,
+                                         skip_unread=self.skip_unread_outputs and not post_nms and n_runs > 1)
         elif self.mc_dropout_enabled and self.num_mc_dropout_runs > 1:
-            if not self.model.use_dropout:
-                raise _cabi.PodError("MC_DROPOUT.ENABLE with DROPOUT_RATE == 0 is not supported")
-            raw, level_off = eng.head_mc(feats, self.num_mc_dropout_runs, seed, image0,
-                                         skip_unread=self.skip_unread_outputs and not post_nms)
+            raise _cabi.PodError("MC_DROPOUT.ENABLE with DROPOUT_RATE == 0 is not supported")
         else:
             raw, level_off = eng.head_eval(feats, members=[0])
         if post_nms:
@@ -238,23 +275,29 @@ class ProbabilisticPredictor:
         return 2 * maps * max(hw) * 256 * 4 + max(hw) * 256 * 4 + samples * anchors * per_anchor * 4
 
     def _infer_chunked(self, feats, image_hw, out_hw, image0, seed, return_candidates, chunk):
-        B = int(feats[0].shape[0])
+        per_member = isinstance(feats[0], (list, tuple))
+        flat = [f for fs in feats for f in fs] if per_member else list(feats)
+        n_lvl = len(feats[0]) if per_member else len(feats)
+        B = int(flat[0].shape[0])
         main = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         bounds = [(c0, min(B, c0 + chunk)) for c0 in range(0, B, chunk)]
 
+        def nest(ts):
+            return [ts[i:i + n_lvl] for i in range(0, len(ts), n_lvl)] if per_member else ts
+
         def stage(c0, c1):
             """Slice of the batch on the device + the event after which it may be read."""
-            if all(f.is_cuda for f in feats):
-                return [f[c0:c1] for f in feats], None
+            if all(f.is_cuda for f in flat):
+                return nest([f[c0:c1] for f in flat]), None
             with torch.cuda.stream(self._copy_stream):
-                dev = [f[c0:c1].to(self.device, dtype=torch.float32, non_blocking=True) for f in feats]
+                dev = [f[c0:c1].to(self.device, dtype=torch.float32, non_blocking=True) for f in flat]
                 ev = torch.cuda.Event()
                 ev.record(self._copy_stream)
             for t in dev:
                 t.record_stream(main)              # allocated on the copy stream, consumed on the compute stream
-            return dev, ev
+            return nest(dev), ev
 
         res, cands, dets = [], [], []
         nxt = stage(*bounds[0])
@@ -280,6 +323,9 @@ class ProbabilisticPredictor:
 
     def _to_instances(self, det, out_hw):
         counts = det["count"].cpu().tolist()
+        # the count read above synchronised the stream: one look at the library's device-side error word per call
+        # (expired bounded barrier wait, activation outside the fp16 split range, non-finite input) -> PodError
+        ops.check_status()
         out = []
         for b, n in enumerate(counts):
             inst = Instances((int(out_hw[0]), int(out_hw[1])))

@@ -2,7 +2,7 @@
 
 Geometry and initialisation follow SURVEY.md section 8(d):
   * FPN maps (B, 256, ceil(H/s), ceil(W/s)) for strides 8..128 of the image padded to a
-    multiple of 128 (detectron2 size_divisibility of the RetinaNet FPN backbone);
+    multiple of 128 (the benchmark geometry SURVEY 8(d) quotes; detectron2 itself pads to 32, see level_shapes);
   * head weight sets keyed like the reference module's state dict
     (reference src/probabilistic_modeling/probabilistic_retinanet.py:401-484): tower convs
     `head.{cls,bbox}_subnet.<i>` with i stepping by 3 when dropout layers are present and
@@ -25,16 +25,44 @@ def padded_size(height, width, divisibility=128):
     return ph, pw
 
 
-def level_shapes(height, width, strides=STRIDES):
-    ph, pw = padded_size(height, width, max(strides))
-    return [(ph // s, pw // s) for s in strides]
+def level_shapes(height, width, strides=STRIDES, divisibility=None):
+    """FPN map sizes.  divisibility None: the benchmark geometry of SURVEY 8(d) / BASELINE.md (frame padded to a
+    multiple of the largest stride, 720x1280 -> 768x1280, 20 460 locations).  divisibility 32: what detectron2's
+    RetinaNet backbone produces (frame padded to the res5 stride; P6 / P7 from stride-2 3x3 convolutions with
+    padding 1: 720x1280 -> 92x160, 46x80, 23x40, 12x20, 6x10 = 19 620 locations), cf. backbone.py."""
+    if divisibility is None:
+        ph, pw = padded_size(height, width, max(strides))
+        return [(ph // s, pw // s) for s in strides]
+    ph, pw = padded_size(height, width, divisibility)
+    shapes = []
+    for s in strides:
+        if s <= divisibility:
+            shapes.append((ph // s, pw // s))
+        else:
+            h, w = shapes[-1]
+            shapes.append(((h - 1) // 2 + 1, (w - 1) // 2 + 1))
+    return shapes
 
 
-def make_features(seed, image_idx, height, width, channels=256, strides=STRIDES, dtype=torch.float32):
-    """FPN maps of ONE image: list of (1, C, Hl, Wl) fp32 CPU tensors."""
+def make_features(seed, image_idx, height, width, channels=256, strides=STRIDES, dtype=torch.float32, divisibility=None):
+    """FPN maps of ONE image: list of (1, C, Hl, Wl) fp32 CPU tensors.  `seed` selects an independent feature set
+    for the same image (ensemble member e uses seed e: every member of the reference has its own backbone)."""
     g = torch.Generator().manual_seed(4321 + 7919 * int(seed) + int(image_idx))
     return [torch.randn((1, channels, h, w), generator=g, dtype=dtype)
-            for (h, w) in level_shapes(height, width, strides)]
+            for (h, w) in level_shapes(height, width, strides, divisibility)]
+
+
+def make_member_features(members, image_idx, height, width, divisibility=None):
+    """Feature maps of ONE image as E ensemble members see it: every member of the reference is a full model with its
+    own backbone (reference probabilistic_inference.py:58-77,499-501), so the maps differ per member while
+    describing the same image -- modelled as a shared component plus a member-specific one (unit variance overall).
+    Returns feats[e][l]."""
+    base = make_features(0, image_idx, height, width, divisibility=divisibility)
+    out = []
+    for e in range(members):
+        own = make_features(100 + e, image_idx, height, width, divisibility=divisibility)
+        out.append([(0.9 * b + 0.4358898943540674 * o).contiguous() for b, o in zip(base, own)])
+    return out
 
 
 def make_head_state_dict(seed, num_classes=7, num_anchors=9, channels=256, num_convs=4,

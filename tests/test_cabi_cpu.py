@@ -54,7 +54,7 @@ def test_struct_layouts_match_header(tmp_path):
 
 
 def test_error_codes_and_messages(lib):
-    assert lib.pod_version() == 1
+    assert lib.pod_version() == 2
     rc = lib.pod_conv3x3_tc(None, None)
     assert rc < 0 and b"null args" in lib.pod_last_error()
     rc = lib.pod_sample_mean_q1(None, 0, 0, 0, None, None)
@@ -101,14 +101,20 @@ def test_reference_config_yaml_surface():
 
 def test_backbone_shapes_and_keys_cpu():
     """The upstream ResNet-50-FPN restatement (library torch ops): detectron2 key coverage and the
-    P3..P7 geometry the head path expects (strides 8..128 of the 128-padded image)."""
+    P3..P7 geometry (detectron2 pads to the res5 stride 32: 100x190 -> 128x192; P6 / P7 are stride-2 3x3 convolutions)."""
     from pod_compare_b200 import backbone as BB
     sd = BB.random_state_dict(0)
     assert sorted(sd) == sorted(BB.expected_keys())
     net = BB.ResNetFPNBackbone(sd, device="cpu")
     img = torch.randint(0, 256, (3, 100, 190), dtype=torch.uint8)
     feats = net([img, img])
-    assert [tuple(f.shape) for f in feats] == [(2, 256, 16, 32), (2, 256, 8, 16), (2, 256, 4, 8), (2, 256, 2, 4), (2, 256, 1, 2)]
+    assert [tuple(f.shape) for f in feats] == [(2, 256, 16, 24), (2, 256, 8, 12), (2, 256, 4, 6), (2, 256, 2, 3), (2, 256, 1, 2)]
+    from pod_compare_b200 import synthetic as S
+    assert [tuple(f.shape[-2:]) for f in feats] == S.level_shapes(100, 190, divisibility=32)
+    # a 1280x720 frame: 736 rows (not 768), as detectron2's RetinaNet backbone produces
+    assert S.level_shapes(720, 1280, divisibility=32) == [(92, 160), (46, 80), (23, 40), (12, 20), (6, 10)]
+    big = BB.ResNetFPNBackbone(sd, device="cpu", size_divisibility=128)
+    assert [tuple(f.shape[-2:]) for f in big([img])] == [(16, 32), (8, 16), (4, 8), (2, 4), (1, 2)]
     assert all(torch.isfinite(f).all() for f in feats)
     assert torch.equal(feats[0][0], feats[0][1])
 

@@ -26,9 +26,9 @@ def _run_case(name):
     hws = [O.unpack_head(S.make_head_state_dict(s, num_classes=pp.num_classes, use_dropout=pp.use_dropout,
                                                 cls_var=pp.cls_var, bbox_cov=pp.bbox_cov, cov_dims=pp.cov_dims), pp)
            for s in seeds]
-    feats = S.make_features(0, img, hw[0], hw[1])
+    feats = C.case_features(name)
     return feats, O.predict(feats, hws, pp, mode, hw, out_hw=out_hw, n_mc=n_mc, seed=seed, image=img,
-                            return_candidates=True, post_nms=C.is_post_nms(name))
+                            return_candidates=True, post_nms=C.is_post_nms(name), mc_single=C.is_mc_single(name))
 
 
 @pytest.mark.parametrize("name", list(C.CASES))
@@ -36,7 +36,8 @@ def test_case_matches_reference_fixture(name, golden_dir):
     torch.set_num_threads(8)   # fixtures were generated with 8 threads (summation order of conv)
     g = np.load(os.path.join(golden_dir, "case_%s.npz" % name))
     feats, (final, cand, det) = _run_case(name)
-    chk = np.array([float(f.double().abs().sum()) for f in feats])
+    flat = [f for fs in feats for f in fs] if isinstance(feats[0], (list, tuple)) else feats
+    chk = np.array([float(f.double().abs().sum()) for f in flat])
     assert np.allclose(chk, g["feats_checksum"], rtol=0, atol=0), "synthetic feature generator drifted"
     exact = torch.get_num_threads() == 8
     cmp = (lambda a, b: np.array_equal(a, b)) if exact else (lambda a, b: np.allclose(a, b, rtol=1e-5, atol=1e-6))
