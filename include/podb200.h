@@ -98,7 +98,8 @@ typedef struct pod_dropout {
  * live_reps (0 = all): only the first live_reps of the samples*passes copies of every image are written
  * (see pod_conv_args.map_live). */
 int pod_mask_expand_split(const float* x, int NB_in, int HW, int C, const pod_dropout* d, float scale,
-                          void* dst_hi, void* dst_lo, int live_reps, void* stream);
+                          void* dst_hi, void* dst_lo, int live_reps, const float* scale_dev /* nullable: replaces scale */,
+                          void* stream);
 
 /* ---- the head convolutions (probabilistic_retinanet.py:401-441,458-484,517-523) -------------
  * 3x3 / stride 1 / pad 1 convolution over NB channels-last maps as an implicit GEMM on the
@@ -148,10 +149,12 @@ typedef struct pod_conv_args {
    * "mean" runs over range(len-1); only box_delta of the last sample is used, :326-331). */
   int map_group;
   int map_live;
-  /* Optional device-resident input scale (a power of two written by pod_pow2_scale_from_absmax); when non-NULL it
-   * replaces in_scale.  Not available for the weights-as-A output convolutions (their inputs are tower activations
-   * with the fixed scale). */
+  /* Optional device-resident split scales (powers of two written by pod_pow2_scale_from_absmax); when non-NULL they
+   * replace in_scale / out_scale.  The engine derives ONE scale per call from max|feature| and uses it for every
+   * activation of the towers, so that inputs of any magnitude stay inside the fp16 split range without a host
+   * round trip (values are computed in fp32 registers in true units; only the stored pair is scaled). */
   const float* in_scale_dev;
+  const float* out_scale_dev;
 } pod_conv_args;
 int pod_conv3x3_tc(const pod_conv_args* a, void* stream);
 /* Channels per pipeline stage of the tcgen05 kernel: 64 (SWIZZLE_128B operand tiles, default) or
@@ -316,6 +319,29 @@ typedef struct pod_merge_args {
   int* out_count;
 } pod_merge_args;
 int pod_cluster_merge(const pod_merge_args* a, void* stream);
+
+/* ---- wire format (inference_utils.py:428-502 covar_xyxy_to_xywh / instances_to_json; src/apply_net.py:53-102) ----
+ * Detections of a whole batch (pod_nms_fuse outputs) -> fixed-size fp32 records, one row of
+ * 1 + max_dets * (4 + 1 + 1 + K + 16) floats per image: count, then per detection box(4) score class probs(K)
+ * cov(16); rows past `count` are zero.
+ *   xywh == 0: boxes xyxy and covariance as they are -- the record of the multi-GPU all-gather;
+ *   xywh == 1: the layout of coco_instances_results.json -- boxes XYWH_ABS, covariance T Sigma T^T
+ *              (T = [[1,0,0,0],[0,1,0,0],[-1,0,1,0],[0,-1,0,1]]), bit-identical to the reference's fp32 arithmetic.
+ * cat_map (device, K ints, nullable): contiguous class id -> dataset category id, -1 = class has no id in the test
+ * dataset (the host writer drops those rows, inference_utils.py:489). */
+typedef struct pod_wire_args {
+  const float* det_boxes;
+  const float* det_cov;
+  const float* det_scores;
+  const int* det_classes;
+  const float* det_probs;
+  const int* det_count;
+  int B, max_dets, K;
+  int xywh;
+  const int* cat_map;
+  float* records;
+} pod_wire_args;
+int pod_wire_records(const pod_wire_args* a, void* stream);
 
 #ifdef __cplusplus
 }

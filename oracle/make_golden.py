@@ -70,6 +70,30 @@ def model_case(name):
     print("case %-20s detections=%3d candidates=%4d" % (name, len(final), boxes.shape[0]))
 
 
+JSON_CASES = ("regclsvar_std", "bayesod_plain", "baseline_std", "mcdrop_pre_n4")
+
+
+def json_case(name):
+    """The reference's own wire format: `instances_to_json` (inference_utils.py:454-502) applied to the final Instances
+    of a case, with the two category mappings src/apply_net.py:53-79 can produce for a BDD-trained model (BDD test
+    set: contiguous id + 1; KITTI test set: only car / person survive).  Stored as JSON text, like the file the
+    reference writes (src/apply_net.py:100-102)."""
+    import json
+    from pod_compare_b200 import wire
+    IU = R.load_reference()["inference_utils"]
+    opts, mode, n_mc, seeds, hw, out_hw, seed, img = C.CASES[name]
+    cfg, pp, sds = state_dicts_for(name)
+    pred = R.build_reference_predictor(cfg, sds if len(sds) > 1 else sds[0])
+    final, _ = R.run_reference(pred, C.case_features(name), hw, out_hw=out_hw, seed=seed, image_idx=img, stage="final")
+    bdd, kitti = wire.BDD_THING_DATASET_ID_TO_CONTIGUOUS_ID, wire.KITTI_THING_DATASET_ID_TO_CONTIGUOUS_ID
+    maps = {"bdd": wire.build_category_mapping("bdd_train", "bdd_val", bdd, bdd),
+            "kitti": wire.build_category_mapping("bdd_train", "kitti_val", bdd, kitti)}
+    out = {k: IU.instances_to_json(final, 1000 + img, m) for k, m in maps.items()}
+    with open(os.path.join(OUT, "json_%s.json" % name), "w") as f:
+        json.dump(out, f, indent=1, separators=(",", ": "))
+    print("json %-20s bdd=%d kitti=%d entries" % (name, len(out["bdd"]), len(out["kitti"])))
+
+
 def planted_cases():
     mods = R.load_reference()
     IU, PI = mods["inference_utils"], mods["inference"]
@@ -114,10 +138,13 @@ def main():
     torch.set_num_threads(8)
     only = [a for a in sys.argv[1:] if not a.startswith("-")]
     for name in (only or C.CASES):
-        if name != "planted":
+        if name not in ("planted", "json"):
             model_case(name)
     if not only or "planted" in only:
         planted_cases()
+    if not only or "json" in only:
+        for name in JSON_CASES:
+            json_case(name)
 
 
 if __name__ == "__main__":

@@ -638,6 +638,26 @@ def detections_to_json(d: Detections, img_id, cat_mapping):
              "cls_prob": probs[k], "bbox_covar": cov[k]} for k in range(n) if classes[k] != -1]
 
 
+def read_results_json(entries, min_allowed_score=0.0):
+    """The READER's side of the wire contract: src/core/evaluation_tools/evaluation_utils.py:28-69
+    (`eval_predictions_preprocess`): skips category -1 and low scores, turns XYWH boxes back into XYXY in float64 numpy and
+    the covariance back with T' = [[1,0,0,0],[0,1,0,0],[1,0,1,0],[0,1,0,1]], then casts to fp32 tensors per image."""
+    boxes, probs, covs = {}, {}, {}
+    Tm = np.array([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [1.0, 0, 1.0, 0], [0, 1.0, 0.0, 1.0]])
+    for e in entries:
+        if e["category_id"] == -1 or np.array(e["cls_prob"]).max(0) < min_allowed_score:
+            continue
+        b = e["bbox"]
+        xyxy = np.array([b[0], b[1], b[0] + b[2], b[1] + b[3]])
+        cov = np.matmul(np.matmul(Tm, np.array(e["bbox_covar"])), Tm.T)
+        k = e["image_id"]
+        boxes.setdefault(k, []).append(torch.as_tensor(xyxy, dtype=torch.float32))
+        probs.setdefault(k, []).append(torch.as_tensor(e["cls_prob"], dtype=torch.float32))
+        covs.setdefault(k, []).append(torch.as_tensor(cov, dtype=torch.float32))
+    return ({k: torch.stack(v) for k, v in boxes.items()}, {k: torch.stack(v) for k, v in probs.items()},
+            {k: torch.stack(v) for k, v in covs.items()})
+
+
 # --------------------------------------------------------------------------------------
 # whole path, one image:  features -> detections   (predictor.__call__, :86-111)
 # --------------------------------------------------------------------------------------

@@ -56,6 +56,7 @@ struct Params {
   int dbg_skip_ld;      // debug: skip the TMEM drains (results invalid) to attribute chunk overhead
   int dbg_fault;        // fault injection (tests): CTA 0's producer never issues its first load -> bounded waits expire
   const float* in_scale_dev;   // optional device-resident input scale (overrides the host value folded into acc_scale)
+  const float* out_scale_dev;  // optional device-resident split scale of the HIDDEN output (overrides out_scale)
   int kb_per_chunk;     // K-blocks summed in the tensor core before an fp32 RN add in registers
   float acc_scale;      // 1 / (in_scale * w_scale)
   float out_scale;
@@ -301,7 +302,8 @@ __device__ __forceinline__ void tile_epilogue(const Params& P, const float (&sum
                                               const uint32_t (&keep)[(NG * 16 + 31) / 32]) {
     // a device-resident input scale (power of two, written by pod_feature_scale) divides exactly
     const float acc_scale = P.in_scale_dev != nullptr ? P.acc_scale / __ldg(P.in_scale_dev) : P.acc_scale;
-    const float sat_limit = 65504.f / P.out_scale;
+    const float out_scale = P.out_scale_dev != nullptr ? __ldg(P.out_scale_dev) : P.out_scale;
+    const float sat_limit = 65504.f / out_scale;
     bool saturated = false;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
@@ -326,8 +328,8 @@ __device__ __forceinline__ void tile_epilogue(const Params& P, const float (&sum
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           __half h0, l0, h1, l1;
-          pod_split_h(v[2 * i] * P.out_scale, h0, l0);
-          pod_split_h(v[2 * i + 1] * P.out_scale, h1, l1);
+          pod_split_h(v[2 * i] * out_scale, h0, l0);
+          pod_split_h(v[2 * i + 1] * out_scale, h1, l1);
           ph[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
           pl[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
         }
@@ -1295,6 +1297,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_wt(const __grid_cons
       const int ch = quad * 32 + lane;
       if (quad < 2 && ch < P.Cout) {
         const float b = __ldg(P.bias + ch);
+        const float acc_scale = P.in_scale_dev != nullptr ? P.acc_scale / __ldg(P.in_scale_dev) : P.acc_scale;
         const long long pstride = P.out_pixel_stride;
         // this thread's 128 columns are 8 rows x 16 columns of the pixel tile
         float* o = P.out_f32 + (long long)n * P.out_map_stride + ch +
@@ -1305,7 +1308,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_wt(const __grid_cons
           if (ty < rows_ok) {
 #pragma unroll
             for (int tx = 0; tx < WT_TILE; ++tx) {
-              float v = fmaf(sum[ty * WT_TILE + tx], P.acc_scale, b);
+              float v = fmaf(sum[ty * WT_TILE + tx], acc_scale, b);
               if (P.relu) v = fmaxf(v, 0.f);
               if (tx < cols_ok) o[tx * pstride] = v;
             }
@@ -1445,7 +1448,6 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   const int BK = g_tc_bk;
   // weights-as-A: RAW mode, <= 64 output channels, single destination, hi|lo weight halves adjacent (stacked along M)
   const bool wt = g_tc_wt && BK == 64 && a->mode == POD_OUT_RAW && a->Cout_pad == 64 && a->out2_f32 == nullptr &&
-                  a->in_scale_dev == nullptr &&
                   (const char*)a->w_lo == (const char*)a->w_hi + (size_t)64 * 9 * a->Cin * 2;
   if (wt) {
     POD_REQUIRE(a->out_f32 && a->out_pixel_stride >= a->Cout, "pod_conv3x3_tc: raw mode needs out_f32 / pixel stride >= Cout");
@@ -1475,7 +1477,8 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
     P.relu = a->relu;
     P.kb_per_chunk = g_tc_taps * (a->Cin / 64);
     if (g_tc_chunk_kb > 0 && (9 * (a->Cin / 64)) % g_tc_chunk_kb == 0) P.kb_per_chunk = g_tc_chunk_kb;
-    P.acc_scale = 1.0f / (a->in_scale * a->w_scale) * trunc_comp_factor(P.kb_per_chunk, 64, 2);
+    P.in_scale_dev = a->in_scale_dev;
+    P.acc_scale = 1.0f / ((a->in_scale_dev ? 1.0f : a->in_scale) * a->w_scale) * trunc_comp_factor(P.kb_per_chunk, 64, 2);
     P.bias = a->bias;
     P.out_f32 = a->out_f32;
     P.out_map_stride = a->out_map_stride; P.out_pixel_stride = a->out_pixel_stride;
@@ -1516,6 +1519,7 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   P.acc_scale = 1.0f / ((a->in_scale_dev ? 1.0f : a->in_scale) * a->w_scale) *
                 trunc_comp_factor(P.kb_per_chunk, BK, a->Cout_pad <= 128 ? 2 : 3);
   P.out_scale = a->out_scale;
+  P.out_scale_dev = a->out_scale_dev;
   P.bias = a->bias;
   P.out_hi = (__half*)a->out_hi; P.out_lo = (__half*)a->out_lo; P.out_f32 = a->out_f32;
   P.out_map_stride = a->out_map_stride; P.out_pixel_stride = a->out_pixel_stride;
@@ -1529,7 +1533,7 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   P.drop_thr = 0;
   P.drop_scale = 1.f;
   if (a->mode == POD_OUT_HIDDEN) {
-    POD_REQUIRE(a->out_hi && a->out_lo && a->out_scale > 0.f, "pod_conv3x3_tc: hidden mode needs out_hi/out_lo/out_scale");
+    POD_REQUIRE(a->out_hi && a->out_lo && (a->out_scale > 0.f || a->out_scale_dev), "pod_conv3x3_tc: hidden mode needs out_hi/out_lo/out_scale");
     POD_REQUIRE(a->Cout == a->Cout_pad, "pod_conv3x3_tc: hidden mode needs Cout == Cout_pad");
     POD_REQUIRE(((uintptr_t)a->out_hi | (uintptr_t)a->out_lo) % 16 == 0, "pod_conv3x3_tc: outputs must be 16-byte aligned");
     if (a->drop.p > 0.0) {

@@ -183,8 +183,9 @@ extern "C" __attribute__((visibility("default"))) int pod_pack_conv_weight_f32(c
 // ---------------------------------------------------------------------------------------------
 // one thread = 8 consecutive channels (two Philox quads): 32-byte loads, 16-byte stores per copy
 __global__ void __launch_bounds__(256)
-k_mask_expand(const float* __restrict__ x, int64_t oct_per_map, int NB_in, pod_dropout d, float scale,
+k_mask_expand(const float* __restrict__ x, int64_t oct_per_map, int NB_in, pod_dropout d, float scale, const float* __restrict__ scale_dev,
               uint32_t thr, float dscale, PhiloxKey key, __half* __restrict__ hi, __half* __restrict__ lo, int live_reps) {
+  if (scale_dev != nullptr) scale = __ldg(scale_dev);
   const int reps = d.samples * d.passes;
   const int64_t total = oct_per_map * NB_in;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -229,7 +230,7 @@ k_mask_expand(const float* __restrict__ x, int64_t oct_per_map, int NB_in, pod_d
 }
 
 extern "C" __attribute__((visibility("default"))) int pod_mask_expand_split(const float* x, int NB_in, int HW, int C, const pod_dropout* d, float scale,
-                                     void* dst_hi, void* dst_lo, int live_reps, void* stream) {
+                                     void* dst_hi, void* dst_lo, int live_reps, const float* scale_dev, void* stream) {
   POD_REQUIRE(x && d && dst_hi && dst_lo && NB_in > 0 && HW > 0 && C > 0 && C % 8 == 0, "pod_mask_expand_split: bad args (C%%8)");
   POD_REQUIRE(d->samples > 0 && d->passes > 0 && d->p > 0.0 && d->p < 1.0, "pod_mask_expand_split: bad dropout spec");
   POD_REQUIRE(live_reps >= 0 && live_reps <= d->samples * d->passes, "pod_mask_expand_split: live_reps out of range");
@@ -238,7 +239,7 @@ extern "C" __attribute__((visibility("default"))) int pod_mask_expand_split(cons
   const int64_t total = qpm * NB_in;
   // 39 registers x 256 threads: six CTAs are resident per SM; a grid of exactly that many leaves no partial last wave
   const int grid = (int)((total + 255) / 256 < (int64_t)pod_num_sms() * 6 ? (total + 255) / 256 : (int64_t)pod_num_sms() * 6);
-  k_mask_expand<<<grid, 256, 0, (cudaStream_t)stream>>>(x, qpm, NB_in, *d, scale, pod_dropout_threshold(d->p),
+  k_mask_expand<<<grid, 256, 0, (cudaStream_t)stream>>>(x, qpm, NB_in, *d, scale, scale_dev, pod_dropout_threshold(d->p),
                                                         pod_dropout_scale(d->p), pod_key(d->seed, POD_STREAM_DROPOUT),
                                                         (__half*)dst_hi, (__half*)dst_lo, live_reps);
   POD_LAUNCH_CHECK();

@@ -16,6 +16,8 @@ def init_from_env(backend=None):
         backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
+        # asynchronous NCCL errors abort the communicator and raise (instead of hanging the other ranks)
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "1")
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, world
 
@@ -33,13 +35,9 @@ def record_width(max_dets, K):
 
 def pack_records(det):
     """det dict of ops.nms_fuse -> (B, 1 + max_dets*(22+K)) fp32: count, then per detection
-    box(4) score(1) class(1) probs(K) cov(16); rows past `count` are zero."""
-    B, D = det["scores"].shape
-    body = torch.cat([det["boxes"], det["scores"].unsqueeze(-1), det["classes"].to(torch.float32).unsqueeze(-1),
-                      det["probs"], det["cov"].reshape(B, D, 16)], dim=2)
-    valid = (torch.arange(D, device=body.device)[None, :] < det["count"][:, None]).unsqueeze(-1)
-    body = torch.where(valid, body, torch.zeros((), dtype=body.dtype, device=body.device))
-    return torch.cat([det["count"].to(torch.float32).unsqueeze(-1), body.reshape(B, -1)], dim=1).contiguous()
+    box(4) score(1) class(1) probs(K) cov(16); rows past `count` are zero.  One launch of pod_wire_records."""
+    from . import ops
+    return ops.wire_records(det, xywh=False)
 
 
 def unpack_records(rec, max_dets, K):
@@ -60,5 +58,12 @@ def all_gather_records(rec):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return rec
     out = torch.empty((dist.get_world_size() * rec.shape[0], rec.shape[1]), dtype=rec.dtype, device=rec.device)
-    dist.all_gather_into_tensor(out, rec)
+    # NCCL reports communicator faults asynchronously (ncclCommGetAsyncError, polled by ProcessGroupNCCL's watchdog,
+    # which init_from_env arms): wait() on the work object is where such a fault -- or a timeout of a dead peer --
+    # surfaces as an exception, at the one collective of the path instead of at some later unrelated CUDA call
+    try:
+        work = dist.all_gather_into_tensor(out, rec, async_op=True)
+        work.wait()
+    except Exception as e:  # noqa: BLE001
+        raise RuntimeError("all-gather of the detection records failed on rank %d: %s" % (dist.get_rank(), e)) from e
     return out

@@ -25,7 +25,10 @@ import torch
 from . import ops
 from ._cabi import POD_OUT_HIDDEN, POD_OUT_RAW, PodError
 
-ACT_SCALE = 16.0          # fp16 split scale of activations: |x| < 4094, abs. resolution 2^-28
+ACT_SCALE = 16.0          # largest fp16 split scale of activations (|x| < 4094, abs. resolution 2^-28); the scale of a call is
+                          # min(ACT_SCALE, largest power of two s with max|feature| * s <= FEATURE_TARGET), a device word
+FEATURE_TARGET = 128.0    # = 8 * ACT_SCALE: stored features stay below 128, leaving 512x headroom (65504 / 128) for hidden
+                          # activations larger than the features; beyond that pod_status reports saturation
 TOWER_CLS, TOWER_BOX = 0, 1
 
 
@@ -143,24 +146,28 @@ class HeadEngine:
     # ------------------------------------------------------------------ head
     @staticmethod
     def feature_scale(feats):
-        """fp16 split scale of the input maps: ACT_SCALE unless a feature exceeds its range (|x|*scale must stay
-        below fp16's 65504), in which case the largest smaller power of two.  Computed by two small kernels into a
-        device word that the layout kernel and the first tower convolution read: no torch ops, no host sync
-        (non-finite inputs raise through ops.check_status at the end of the call)."""
-        return ops.feature_scale_dev(feats, ACT_SCALE, 32768.0)
+        """fp16 split scale of EVERY activation of this call (features and tower layers): ACT_SCALE when
+        max|feature| <= 8 (e.g. unit-variance maps), otherwise the largest smaller power of two that keeps the stored
+        features below FEATURE_TARGET.  Values are computed in fp32 registers in true units and only the stored
+        (hi, lo) pair is scaled, so results do not depend on the scale beyond fp16 round-off; a power-of-two scale
+        makes the rescaling exact.  Computed by two small kernels into a device word that every kernel of the call
+        reads: no torch ops, no host sync (non-finite inputs raise through ops.check_status at the end of the call)."""
+        return ops.feature_scale_dev(feats, ACT_SCALE, FEATURE_TARGET)
 
-    def _conv_hidden(self, src, NB, H, W, pcv, dst, drop, in_scale=ACT_SCALE, map_group=0, map_live=0, in_scale_dev=None):
-        ops.conv3x3_tc(src[0], src[1], in_scale, NB, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, pcv.cout,
-                       pcv.cout_pad, POD_OUT_HIDDEN, True, out_hi=dst[0], out_lo=dst[1], out_scale=ACT_SCALE, drop=drop,
-                       map_group=map_group, map_live=map_live, in_scale_dev=in_scale_dev)
+    def _conv_hidden(self, src, NB, H, W, pcv, dst, drop, scale_dev, map_group=0, map_live=0):
+        """256 -> 256 tower layer; `scale_dev` is the call's activation scale (input and output pairs)."""
+        ops.conv3x3_tc(src[0], src[1], 1.0, NB, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, pcv.cout,
+                       pcv.cout_pad, POD_OUT_HIDDEN, True, out_hi=dst[0], out_lo=dst[1], out_scale=1.0, drop=drop,
+                       map_group=map_group, map_live=map_live, in_scale_dev=scale_dev, out_scale_dev=scale_dev)
 
-    def _conv_out(self, src, NB, H, W, blocks, out, out_offset, out_map_stride, in_map_stride=None, in_offset=0,
+    def _conv_out(self, src, NB, H, W, blocks, out, out_offset, out_map_stride, scale_dev, in_map_stride=None, in_offset=0,
                   map_group=0, map_live=0):
         for pcv in blocks:
-            ops.conv3x3_tc(src[0], src[1], ACT_SCALE, NB, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, pcv.cout,
+            ops.conv3x3_tc(src[0], src[1], 1.0, NB, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, pcv.cout,
                            pcv.cout_pad, POD_OUT_RAW, False, out_f32=out, out_offset=out_offset + pcv.col0,
                            out_map_stride=out_map_stride, out_pixel_stride=pcv.total_cout,
-                           in_map_stride=in_map_stride, in_offset=in_offset, map_group=map_group, map_live=map_live)
+                           in_map_stride=in_map_stride, in_offset=in_offset, map_group=map_group, map_live=map_live,
+                           in_scale_dev=scale_dev)
 
     def head_mc(self, feats, n_mc, seed, image0, skip_unread=False):
         """MC-dropout head loop: feats = list over levels of (B,256,H,W) fp32.
@@ -212,25 +219,26 @@ class HeadEngine:
                 live = grp
                 if skip_unread and n_mc > 1:
                     live = (n_mc - 1) * t_passes + (0 if tower == TOWER_CLS else 1)
-                ops.mask_expand_split(c1[: B * HW * 256].view(B, HW, 256), d0, ACT_SCALE, act[0][0], act[0][1], live_reps=live)
+                ops.mask_expand_split(c1[: B * HW * 256].view(B, HW, 256), d0, 1.0, act[0][0], act[0][1], live_reps=live,
+                                      scale_dev=fscale)
                 cur = 0
                 NB = B * n_mc * t_passes
                 for layer in range(1, len(tw)):
                     d = ops.make_dropout(pc.dropout_rate, seed, image0, n_mc, t_passes, 0, tower, layer, lvl)
-                    self._conv_hidden(act[cur], NB, H, W, tw[layer], act[cur ^ 1], d, map_group=grp, map_live=live)
+                    self._conv_hidden(act[cur], NB, H, W, tw[layer], act[cur ^ 1], d, fscale, map_group=grp, map_live=live)
                     cur ^= 1
                 n_live = n_mc - 1 if (skip_unread and n_mc > 1) else n_mc        # samples whose mean/var heads are read
                 # output convs: pass-0 maps feed the mean head, pass-1 maps the variance head (Q2)
                 mean_pc, var_pc = (w.cls_score, w.cls_var) if tower == TOWER_CLS else (w.bbox_pred, w.bbox_cov)
                 mean_out = raw["logits"] if tower == TOWER_CLS else raw["deltas"]
                 D = mean_pc[0].total_cout // A
-                self._conv_out(act[cur], B * n_mc, H, W, mean_pc, mean_out, level_off[lvl] * D, R * D,
+                self._conv_out(act[cur], B * n_mc, H, W, mean_pc, mean_out, level_off[lvl] * D, R * D, fscale,
                                in_map_stride=t_passes * HW * 256, in_offset=0, map_group=n_mc,
                                map_live=n_live if tower == TOWER_CLS else n_mc)
                 if has_var:
                     var_out = raw["logvar"] if tower == TOWER_CLS else raw["regvar"]
                     Dv = var_pc[0].total_cout // A
-                    self._conv_out(act[cur], B * n_mc, H, W, var_pc, var_out, level_off[lvl] * Dv, R * Dv,
+                    self._conv_out(act[cur], B * n_mc, H, W, var_pc, var_out, level_off[lvl] * Dv, R * Dv, fscale,
                                    in_map_stride=2 * HW * 256, in_offset=HW * 256, map_group=n_mc, map_live=n_live)
         return raw, level_off
 
@@ -281,7 +289,7 @@ class HeadEngine:
                     tw = w.towers[tower]
                     src, cur = (fhi, flo), 0
                     for layer in range(len(tw)):
-                        self._conv_hidden(src, B, H, W, tw[layer], act[cur], None, in_scale_dev=fscale if layer == 0 else None)
+                        self._conv_hidden(src, B, H, W, tw[layer], act[cur], None, fscale)
                         src = act[cur]
                         cur ^= 1
                     mean_pc, var_pc = (w.cls_score, w.cls_var) if tower == TOWER_CLS else (w.bbox_pred, w.bbox_cov)
@@ -293,18 +301,18 @@ class HeadEngine:
                         Dv = var_pc[0].total_cout // A
                         split = mean_pc[0].total_cout
                         for pcv in fused:
-                            ops.conv3x3_tc(src[0], src[1], ACT_SCALE, B, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias,
-                                           pcv.cout, pcv.cout_pad, POD_OUT_RAW, False,
+                            ops.conv3x3_tc(src[0], src[1], 1.0, B, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias,
+                                           pcv.cout, pcv.cout_pad, POD_OUT_RAW, False, in_scale_dev=fscale,
                                            out_f32=mean_out, out_offset=(e * R + level_off[lvl]) * D + pcv.col0,
                                            out_map_stride=E * R * D, out_pixel_stride=A * D,
                                            out2_f32=var_out, out2_offset=(e * R + level_off[lvl]) * Dv,
                                            split_col=split - pcv.col0, out2_map_stride=E * R * Dv, out2_pixel_stride=A * Dv)
                         continue
-                    self._conv_out(src, B, H, W, mean_pc, mean_out, (e * R + level_off[lvl]) * D, E * R * D)
+                    self._conv_out(src, B, H, W, mean_pc, mean_out, (e * R + level_off[lvl]) * D, E * R * D, fscale)
                     if var_pc is not None:
                         var_out = raw["logvar"] if tower == TOWER_CLS else raw["regvar"]
                         Dv = var_pc[0].total_cout // A
-                        self._conv_out(src, B, H, W, var_pc, var_out, (e * R + level_off[lvl]) * Dv, E * R * Dv)
+                        self._conv_out(src, B, H, W, var_pc, var_out, (e * R + level_off[lvl]) * Dv, E * R * Dv, fscale)
         return raw, level_off
 
     # ------------------------------------------------------------------ statistics + post-processing

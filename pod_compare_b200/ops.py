@@ -10,8 +10,8 @@ import math
 import torch
 
 from . import _cabi
-from ._cabi import (POD_OUT_HIDDEN, POD_OUT_RAW, ConvArgs, DecodeArgs, Dropout, MergeArgs, NmsArgs, check, int_array, ptr,
-                    stream_ptr)
+from ._cabi import (POD_OUT_HIDDEN, POD_OUT_RAW, ConvArgs, DecodeArgs, Dropout, MergeArgs, NmsArgs, WireArgs, check, int_array,
+                    ptr, stream_ptr)
 
 _launches = 0
 PROFILE = None      # bench.py sets this to a list: (start_event, end_event, algorithmic FLOPs, tag) per conv launch
@@ -147,7 +147,7 @@ def pack_conv_weight_f32(w, cout_pad):
     return out
 
 
-def mask_expand_split(x, drop, scale, out_hi=None, out_lo=None, live_reps=0):
+def mask_expand_split(x, drop, scale, out_hi=None, out_lo=None, live_reps=0, scale_dev=None):
     """x (NB, HW, C) fp32 -> (NB*samples*passes, HW, C) fp16 split pair.  live_reps > 0: only the first
     live_reps copies of every image are written (the others are never read, see conv3x3_tc map_live)."""
     lib = _cabi.require_device()
@@ -162,7 +162,7 @@ def mask_expand_split(x, drop, scale, out_hi=None, out_lo=None, live_reps=0):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     check(lib.pod_mask_expand_split(ptr(x), NB, HW, Cn, C.byref(drop), scale, ptr(out_hi), ptr(out_lo), int(live_reps),
-                                    stream_ptr()), "pod_mask_expand_split")
+                                    ptr(scale_dev), stream_ptr()), "pod_mask_expand_split")
     if PROFILE is not None:
         e1.record()
         PROFILE.append((e0, e1, 4.0 * NB * HW * Cn * (1 + (live_reps or reps)), "mask_expand"))   # 1 read + live writes
@@ -173,7 +173,7 @@ def mask_expand_split(x, drop, scale, out_hi=None, out_lo=None, live_reps=0):
 def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias, Cout, Cout_pad, mode, relu,
                out_hi=None, out_lo=None, out_scale=1.0, out_f32=None, out_map_stride=0, out_pixel_stride=0,
                drop=None, in_map_stride=None, in_offset=0, out_offset=0, out2_f32=None, out2_offset=0, split_col=0,
-               out2_map_stride=0, out2_pixel_stride=0, map_group=0, map_live=0, in_scale_dev=None):
+               out2_map_stride=0, out2_pixel_stride=0, map_group=0, map_live=0, in_scale_dev=None, out_scale_dev=None):
     """Raw-pointer launch of the tcgen05 convolution. `in_offset`/`out_offset` are ELEMENT offsets
     into in_hi/in_lo and out_f32.  in_scale_dev: 1-element fp32 CUDA tensor replacing in_scale."""
     lib = _cabi.require_device()
@@ -198,6 +198,7 @@ def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias,
         a.split_col, a.out2_map_stride, a.out2_pixel_stride = split_col, out2_map_stride, out2_pixel_stride
     a.map_group, a.map_live = int(map_group), int(map_live)
     a.in_scale_dev = in_scale_dev.data_ptr() if in_scale_dev is not None else None
+    a.out_scale_dev = out_scale_dev.data_ptr() if out_scale_dev is not None else None
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -459,5 +460,34 @@ def cluster_merge(det, runs, affinity):
     a.out_boxes, a.out_cov, a.out_scores = out["boxes"].data_ptr(), out["cov"].data_ptr(), out["scores"].data_ptr()
     a.out_classes, a.out_probs, a.out_count = out["classes"].data_ptr(), out["probs"].data_ptr(), out["count"].data_ptr()
     check(lib.pod_cluster_merge(C.byref(a), stream_ptr()), "pod_cluster_merge")
+    _count()
+    return out
+
+
+def record_width(max_dets, K):
+    return 1 + max_dets * (4 + 1 + 1 + K + 16)
+
+
+def wire_records(det, xywh=False, cat_map=None, out=None):
+    """Detections of a batch (dict of nms_fuse) -> (B, 1 + max_dets*(22+K)) fp32 records in one launch.
+    xywh=False: the all-gather record (xyxy boxes, covariance as is); xywh=True: the reference's JSON layout
+    (XYWH boxes, T Sigma T^T).  cat_map: int32 CUDA tensor (K,) contiguous class -> dataset category id (-1 = none)."""
+    lib = _cabi.require_device()
+    B, D, K = det["probs"].shape
+    if out is None:
+        out = torch.empty((B, record_width(D, K)), dtype=torch.float32, device=det["probs"].device)
+    a = WireArgs()
+    a.det_boxes = _chk(det["boxes"], torch.float32, "boxes").data_ptr()
+    a.det_cov = _chk(det["cov"], torch.float32, "cov").data_ptr()
+    a.det_scores = _chk(det["scores"], torch.float32, "scores").data_ptr()
+    a.det_classes = _chk(det["classes"], torch.int32, "classes").data_ptr()
+    a.det_probs = _chk(det["probs"], torch.float32, "probs").data_ptr()
+    a.det_count = _chk(det["count"], torch.int32, "count").data_ptr()
+    a.B, a.max_dets, a.K, a.xywh = B, D, K, int(bool(xywh))
+    a.cat_map = _chk(cat_map, torch.int32, "cat_map").data_ptr() if cat_map is not None else None
+    if cat_map is not None and cat_map.numel() != K:
+        raise _cabi.PodError("cat_map must have one entry per class")
+    a.records = _chk(out, torch.float32, "records").data_ptr()
+    check(lib.pod_wire_records(C.byref(a), stream_ptr()), "pod_wire_records")
     _count()
     return out

@@ -12,8 +12,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from pod_compare_b200 import distributed as D
-from pod_compare_b200.inference_utils import covar_xyxy_to_xywh, instances_to_json
-from pod_compare_b200.structures import Boxes, Instances
+from pod_compare_b200 import wire
+
+
+def _pack_cpu(det):
+    """Layout of pod_wire_records(xywh=0) restated with torch ops (the product packs on the GPU; the CPU suite only
+    needs records to push through the sharding / gather / unpack plumbing)."""
+    B, D_ = det["scores"].shape
+    body = torch.cat([det["boxes"], det["scores"].unsqueeze(-1), det["classes"].to(torch.float32).unsqueeze(-1),
+                      det["probs"], det["cov"].reshape(B, D_, 16)], dim=2)
+    valid = (torch.arange(D_)[None, :] < det["count"][:, None]).unsqueeze(-1)
+    body = torch.where(valid, body, torch.zeros((), dtype=body.dtype))
+    return torch.cat([det["count"].to(torch.float32).unsqueeze(-1), body.reshape(B, -1)], dim=1).contiguous()
 
 
 def _fake_det(B, D_, K, seed):
@@ -36,7 +46,7 @@ def test_shard_range_partitions_the_batch():
 
 def test_pack_unpack_roundtrip():
     det = _fake_det(3, 100, 7, 0)
-    rec = D.pack_records(det)
+    rec = _pack_cpu(det)
     assert rec.shape == (3, D.record_width(100, 7))
     out = D.unpack_records(rec, 100, 7)
     for b in range(3):
@@ -52,7 +62,7 @@ def _worker(rank, world, port, q):
     os.environ.update({"RANK": str(rank), "WORLD_SIZE": str(world), "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port)})
     D.init_from_env("gloo")
     det = _fake_det(2, 100, 7, 100 + rank)
-    rec = D.pack_records(det)
+    rec = _pack_cpu(det)
     allrec = D.all_gather_records(rec)
     q.put((rank, allrec.numpy()))
     dist.barrier()
@@ -70,24 +80,44 @@ def test_all_gather_records_world2_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    want = torch.cat([D.pack_records(_fake_det(2, 100, 7, 100 + r)) for r in range(2)], 0).numpy()
+    want = torch.cat([_pack_cpu(_fake_det(2, 100, 7, 100 + r)) for r in range(2)], 0).numpy()
     assert np.array_equal(got[0], want) and np.array_equal(got[1], want)   # rank order == image order
 
 
-def test_instances_to_json_schema_and_covariance_transform():
-    inst = Instances((720, 1280))
-    inst.pred_boxes = Boxes(torch.tensor([[10.0, 20.0, 110.0, 220.0], [0.0, 0.0, 5.0, 5.0]]))
-    inst.scores = torch.tensor([0.9, 0.2])
-    inst.pred_classes = torch.tensor([2, 5])
-    inst.pred_cls_probs = torch.rand((2, 7))
-    A = torch.rand((2, 4, 4))
-    inst.pred_boxes_covariance = A @ A.transpose(1, 2)
-    out = instances_to_json(inst, 42, {2: 3})          # class 5 has no dataset id -> dropped
-    assert len(out) == 1
+def test_records_to_json_schema_and_filtering():
+    """Host half of the wire format: records already in the JSON layout (what pod_wire_records(xywh=1) writes) ->
+    the reference's result dicts (inference_utils.py:486-500): schema, image order, category -1 dropped."""
+    K, D_ = 7, 5
+    w = 22 + K
+    rec = np.zeros((3, 1 + D_ * w), np.float32)
+    rng = np.random.RandomState(0)
+    rec[0, 0] = 2
+    rec[0, 1:1 + 2 * w] = rng.rand(2 * w).astype(np.float32)
+    rec[0, 1 + 5] = 3.0               # category ids
+    rec[0, 1 + w + 5] = -1.0          # no id in the test dataset -> dropped
+    rec[2, 0] = 1
+    rec[2, 1:1 + w] = rng.rand(w).astype(np.float32)
+    rec[2, 1 + 5] = 1.0
+    out = wire.records_to_json(rec, ["a", "b", "c"], K, D_)
+    assert [r["image_id"] for r in out] == ["a", "c"]
     r = out[0]
     assert set(r) == {"image_id", "category_id", "bbox", "score", "cls_prob", "bbox_covar"}
-    assert r["image_id"] == 42 and r["category_id"] == 3 and r["bbox"] == [10.0, 20.0, 100.0, 200.0]
-    T = torch.tensor([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [-1.0, 0, 1.0, 0], [0, -1.0, 0, 1.0]])
-    want = T @ inst.pred_boxes_covariance[0] @ T.T
-    assert torch.allclose(torch.tensor(r["bbox_covar"]), want, atol=1e-6)
-    assert torch.allclose(covar_xyxy_to_xywh(inst.pred_boxes_covariance)[0], want, atol=1e-6)
+    assert r["category_id"] == 3 and isinstance(r["category_id"], int)
+    assert r["bbox"] == rec[0, 1:5].tolist() and r["score"] == float(rec[0, 5])
+    assert r["cls_prob"] == rec[0, 7:7 + K].tolist() and np.array_equal(np.array(r["bbox_covar"], np.float32).ravel(), rec[0, 7 + K:1 + w])
+    import json
+    json.dumps(out)                     # plain Python numbers only
+
+
+def test_category_mapping_follows_apply_net():
+    """src/apply_net.py:53-79 with the reference's own tables (src/core/datasets/metadata.py)."""
+    bdd, kitti = wire.BDD_THING_DATASET_ID_TO_CONTIGUOUS_ID, wire.KITTI_THING_DATASET_ID_TO_CONTIGUOUS_ID
+    same = wire.build_category_mapping("bdd_train", "bdd_val", bdd, bdd)
+    assert same == {i: i + 1 for i in range(7)}
+    cross = wire.build_category_mapping("bdd_train", "kitti_val", bdd, kitti)
+    assert cross == {0: 1, 3: 2}        # BDD car -> KITTI id 1, BDD person -> KITTI id 2; every other class is dropped
+    m = wire.category_map_tensor(cross, 7, "cpu")
+    assert m.tolist() == [1, -1, -1, 2, -1, -1, -1]
+    import pytest
+    with pytest.raises(ValueError):
+        wire.build_category_mapping("lyft_train", "kitti_val", bdd, kitti)
