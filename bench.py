@@ -80,6 +80,13 @@ def build_cfg(n_mc, workload="mc_pre"):
     return cfg
 
 
+def head_state_dicts(members, use_dropout, cls_var, bbox_cov):
+    """Synthetic weight sets of a workload: one random head, or E correlated members of an ensemble (both arms)."""
+    from pod_compare_b200 import synthetic as S
+    kw = dict(num_classes=7, use_dropout=use_dropout, cls_var=cls_var, bbox_cov=bbox_cov)
+    return S.make_member_state_dicts(members, **kw) if members > 1 else [S.make_head_state_dict(0, **kw)]
+
+
 def workload_config(args, world):
     desc, _, mc, members = WORKLOADS[args.workload]
     return {"workload": "%s, %s, batch %d per GPU, 1280x720 (FPN features in, detections out)"
@@ -88,6 +95,10 @@ def workload_config(args, world):
             "image": "%dx%d" % (WIDTH, HEIGHT), "chunk_images": args.chunk,
             "parallelism": "image-sharded dp%d + NCCL all-gather of detections" % world,
             "l2": "working set per step (tens of GB of activations) far exceeds the 126 MB L2; no flush needed",
+            "sample_mean": ("per-sample output convolutions, outputs averaged (as the reference evaluates it)"
+                            if (getattr(args, "no_fuse_q1", False) or getattr(args, "keep_unread", False) or not mc) else
+                            "last tower layer accumulated over the samples in the conv epilogue; cls_score / cls_var / bbox_cov "
+                            "run once per image (mean of a linear head = head of the mean; fp32 round-off apart, same result)"),
             "unread_outputs": ("evaluated" if getattr(args, "keep_unread", False) else
                                "left out: box_cls / box_cls_var / box_reg_var of the last sample are never read by the "
                                "reference (probabilistic_inference.py:216-267); detections are bit-identical either way")}
@@ -150,8 +161,7 @@ def reference_steps(n_mc, workload, steps, warmup, threads=None, budget_s=REF_TI
     desc_w, _, mc, members = WORKLOADS[workload]
     m = cfg.MODEL.PROBABILISTIC_MODELING
     use_dropout, cls_var, bbox_cov = m.DROPOUT_RATE != 0.0, m.CLS_VAR_LOSS.NAME != "none", m.BBOX_COV_LOSS.NAME != "none"
-    sds = [S.make_head_state_dict(1000 * e, num_classes=7, use_dropout=use_dropout, cls_var=cls_var, bbox_cov=bbox_cov)
-           for e in range(members)]
+    sds = head_state_dicts(members, use_dropout, cls_var, bbox_cov)
     import torchvision          # first use pulls in seconds of lazy imports: keep them out of the timing
     torchvision.ops.nms(torch.tensor([[0.0, 0.0, 1.0, 1.0]]), torch.tensor([1.0]), 0.5)
     from oracle import ref_runner as R
@@ -251,6 +261,9 @@ def main():
     ap.add_argument("--keep-unread", action="store_true",
                     help="also evaluate the last sample's class / variance tower passes, whose outputs the reference "
                          "computes but never reads (default: left out, results identical)")
+    ap.add_argument("--no-fuse-q1", action="store_true",
+                    help="evaluate cls_score / cls_var / bbox_cov for every MC sample and average the outputs (as the reference "
+                         "does) instead of accumulating the last tower layer over the samples (default: fused)")
     ap.add_argument("--halo", type=int, default=-1, help="row-halo activation staging: bit 0 = pixels-as-M kernels, bit 1 = weights-as-A kernel (default 3)")
     ap.add_argument("--chunk-taps", type=int, default=0, help="taps per accumulation chunk (1, 3, 9)")
     ap.add_argument("--chunk-kblocks", type=int, default=0, help="K-blocks per accumulation chunk (overrides --chunk-taps)")
@@ -287,19 +300,28 @@ def main():
     pred = build_predictor(cfg)
     m = pred.model
     members = WORKLOADS[args.workload][3]
-    sds = [S.make_head_state_dict(1000 * e, num_classes=7, use_dropout=m.use_dropout, cls_var=m.compute_cls_var,
-                                  bbox_cov=m.compute_bbox_cov) for e in range(members)]
+    sds = head_state_dicts(members, m.use_dropout, m.compute_cls_var, m.compute_bbox_cov)
     pred.load_weight_sets(sds if members > 1 else sds[0])
     pred.skip_unread_outputs = not args.keep_unread
+    pred.fuse_sample_mean = not args.no_fuse_q1
     B = args.batch
     # synthetic FPN features of this rank's images (weak scaling: B images per GPU)
     img0 = rank * B
     host_feats = None
-    per = [S.make_features(0, img0 + i % 4, HEIGHT, WIDTH) for i in range(min(B, 4))]     # 4 distinct images, tiled
-    host_feats = [torch.cat([per[i % len(per)][l] for i in range(B)], 0).pin_memory() for l in range(5)]
-    dev_feats = [f.cuda(non_blocking=True) for f in host_feats]
+    # every image of the batch is distinct (seeded by its global image id)
+    if members > 1:
+        # ensembles: every member is a full model with its own backbone, hence its own feature maps (feats[e][l])
+        per = [S.make_member_features(members, img0 + i, HEIGHT, WIDTH) for i in range(B)]
+        host_feats = [[torch.cat([per[i][e][l] for i in range(B)], 0).pin_memory() for l in range(5)] for e in range(members)]
+        dev_feats = [[f.cuda(non_blocking=True) for f in fs] for fs in host_feats]
+        h2d_bytes = sum(f.numel() * 4 for fs in host_feats for f in fs)
+    else:
+        per = [S.make_features(0, img0 + i, HEIGHT, WIDTH) for i in range(B)]
+        host_feats = [torch.cat([per[i][l] for i in range(B)], 0).pin_memory() for l in range(5)]
+        dev_feats = [f.cuda(non_blocking=True) for f in host_feats]
+        h2d_bytes = sum(f.numel() * 4 for f in host_feats)
+    del per
     torch.cuda.synchronize()
-    h2d_bytes = sum(f.numel() * 4 for f in host_feats)
 
     def step(feats):
         # one public-API call per step: the predictor evaluates the batch in chunks of args.chunk images and, for
@@ -388,7 +410,7 @@ def main():
                 h[0] += d; h[1] += flop; h[2] += 1
                 continue
             all_ms += d
-            if tag == "tower256":
+            if tag in ("tower256", "tower256_q1"):
                 tot_ms += d
                 tot_flop += flop
                 n += 1

@@ -155,6 +155,22 @@ typedef struct pod_conv_args {
    * round trip (values are computed in fp32 registers in true units; only the stored pair is scaled). */
   const float* in_scale_dev;
   const float* out_scale_dev;
+  /* Optional Q1 sample accumulation (POD_OUT_HIDDEN, 256 channels, CTA-pair kernel): the NB maps are
+   * images x q1_samples x q1_passes (sample-major, pass-minor).  For every pass p whose bit is set in q1_acc_mask the
+   * layer's output is NOT written per sample; instead the reference's sample sum  2*y_0 + y_1 + ... + y_{L-1}
+   * (probabilistic_inference.py:214-270, quirk Q1; L = q1_live[p] samples are evaluated, the others are neither
+   * computed nor read) is accumulated in fp32 into
+   *     q1_acc[((image * n_acc + a) * G + g) * H*W*Cout + pixel*Cout + c],   a = index of p among the accumulated passes,
+   * as G = ceil(q1_samples / q1_group) partial sums over consecutive groups of q1_group samples (a fixed group size
+   * keeps the summation order independent of the batch).  pod_q1_finish adds the partial sums, divides by q1_samples
+   * and writes the split pair that the (linear) output convolutions cls_score / cls_var / bbox_cov then read ONCE per
+   * image:  mean_s conv(x_s) == conv(mean_s x_s).  Passes not in the mask are written per sample as usual
+   * (bbox_pred: every sample's deltas enter the epistemic covariance, :326-331).  q1_acc == NULL: off. */
+  float* q1_acc;
+  int q1_samples, q1_passes;
+  int q1_live[2];
+  int q1_acc_mask;
+  int q1_group;
 } pod_conv_args;
 int pod_conv3x3_tc(const pod_conv_args* a, void* stream);
 /* Channels per pipeline stage of the tcgen05 kernel: 64 (SWIZZLE_128B operand tiles, default) or
@@ -194,6 +210,11 @@ int pod_conv3x3_tc_debug_fault(int on);
 int pod_conv3x3_simt(const float* in, int NB, int H, int W, int Cin, const float* w_kc, const float* bias,
                      int Cout, int Cout_pad, int relu, const pod_dropout* drop, float* out,
                      int64_t out_map_stride, int64_t out_pixel_stride, void* stream);
+
+/* Second half of the Q1 sample accumulation: acc (n_maps, groups, n) fp32 partial sums -> (n_maps, n) split pair of
+ * ((g_0 + g_1) + ...) / samples, scaled by *scale_dev (or `scale` when scale_dev is NULL). */
+int pod_q1_finish(const float* acc, int n_maps, int groups, int64_t n, int samples, float scale, const float* scale_dev,
+                  void* dst_hi, void* dst_lo, void* stream);
 
 /* ---- per-anchor sample statistics (probabilistic_inference.py:214-270, quirk Q1) -------------
  * x (B, S, n) fp32 -> out (B, n):  ((x0 + x0) + x1 + ... + x_{S-2}) / S  in that fp32 order

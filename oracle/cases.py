@@ -58,7 +58,8 @@ CASES = {
     "regclsvar_rpnw": (_VAR + _mode("standard_nms") + ["MODEL.RPN.BBOX_REG_WEIGHTS", (2.0, 2.0, 1.5, 1.5)], "standard_nms", 1,
                        [1000], (96, 160), (96, 160), 26, 15),
     "fullcov_mc_n3": (_VAR + _FULL + _DROP + _mode("mc_dropout_ensembles") + _mc(3), "mc_dropout_ensembles", 3, [3000],
-                      (96, 160), (96, 160), 19, 8),
+                      (96, 160), (96, 160), 29, 8),   # seed chosen so that no two candidates tie exactly (torch.topk leaves
+                                                      # the order of equal scores unspecified; the oracle defines lower index first)
 }
 
 

@@ -11,8 +11,9 @@ in-register (pod_compare_b200/csrc/philox.cuh).  This file is the CPU side of
 that contract; only tests/, bench.py's cpu_baseline leg and smoke() import it.
 
 Stream layout (key = (seed_lo, seed_hi ^ STREAM), counter = (c0, c1, c2, c3)):
-  STREAM_DROPOUT : c0 = (pixel*C + channel)//4, c1 = level | layer<<8 | tower<<16 | pass<<24,
-                   c2 = sample, c3 = image; word i -> channel 4*c0%C + i; keep iff word >= floor(p*2^32)
+  STREAM_DROPOUT : c0 = (pixel*C + channel)//8, c1 = level | layer<<8 | tower<<16 | pass<<24,
+                   c2 = sample, c3 = image; 16 random bits per decision: lane i (0..7) = bits [16*(i%2), +16) of word
+                   i//2 -> element 8*c0 + i; keep iff lane >= floor(p*2^16)  (P(keep) within 1.5e-5 of 1 - p)
   STREAM_LOGIT   : c0 = (anchor*K + k)//4 (row-major over (HWA, K) of one level), c1 = level | run<<8,
                    c2 = draw j, c3 = image; 4 words -> 4 normals (two Box-Muller pairs)
   STREAM_BOX     : c0 = global anchor id (level offset + index in level), c1 = run,
@@ -73,18 +74,20 @@ def box_muller(wa, wb):
 
 
 def dropout_threshold(p):
-    return int(np.floor(float(p) * 4294967296.0)) & 0xFFFFFFFF
+    """16-bit lane threshold: keep iff lane >= floor(p * 2^16)."""
+    return min(int(np.floor(float(p) * 65536.0)), 65535)
 
 
 def dropout_keep_mask(seed, image, sample, pass_, tower, layer, level, H, W, C, p):
     """Boolean keep-mask of shape (H, W, C) (channels-last element order)."""
-    assert C % 4 == 0
+    assert C % 8 == 0
     k0, k1 = _key(seed, STREAM_DROPOUT)
-    n = H * W * C // 4
+    n = H * W * C // 8
     c1 = (level & 0xFF) | ((layer & 0xFF) << 8) | ((tower & 0xFF) << 16) | ((pass_ & 0xFF) << 24)
     w = philox4x32(np.arange(n, dtype=np.uint64), c1, sample, image, k0, k1)
-    words = np.stack(w, axis=1).reshape(H, W, C)
-    return words >= np.uint32(dropout_threshold(p))
+    words = np.stack(w, axis=1)                                              # (n, 4) uint32
+    lanes = np.stack([words & np.uint32(0xFFFF), words >> np.uint32(16)], axis=2)   # (n, 4, 2): low half first
+    return lanes.reshape(H, W, C) >= np.uint32(dropout_threshold(p))
 
 
 def logit_normals(seed, image, level, draws, n_anchor, K, run=0):

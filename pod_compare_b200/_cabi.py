@@ -17,7 +17,7 @@ EXPORTS = [
     "pod_nchw_to_nhwc_split", "pod_nchw_to_nhwc_f32", "pod_pack_conv_weight", "pod_pack_conv_weight_f32",
     "pod_mask_expand_split", "pod_conv3x3_tc", "pod_conv3x3_tc_set_kblock", "pod_conv3x3_tc_set_chunk_taps", "pod_conv3x3_tc_set_chunk_kblocks", "pod_conv3x3_tc_set_pair", "pod_conv3x3_tc_set_halo", "pod_conv3x3_tc_set_wt", "pod_conv3x3_tc_set_trunc_comp", "pod_conv3x3_tc_status",
     "pod_conv3x3_simt", "pod_sample_mean_q1", "pod_scores", "pod_topk_levels", "pod_decode_cov", "pod_nms_fuse",
-    "pod_cluster_merge", "pod_wire_records",
+    "pod_cluster_merge", "pod_wire_records", "pod_q1_finish",
 ]
 
 POD_OUT_HIDDEN, POD_OUT_RAW = 0, 1
@@ -41,7 +41,9 @@ class ConvArgs(C.Structure):
                 ("out_map_stride", C.c_int64), ("out_pixel_stride", C.c_int64), ("drop", Dropout),
                 ("out2_f32", C.c_void_p), ("split_col", C.c_int), ("out2_map_stride", C.c_int64),
                 ("out2_pixel_stride", C.c_int64), ("map_group", C.c_int), ("map_live", C.c_int),
-                ("in_scale_dev", C.c_void_p), ("out_scale_dev", C.c_void_p)]
+                ("in_scale_dev", C.c_void_p), ("out_scale_dev", C.c_void_p),
+                ("q1_acc", C.c_void_p), ("q1_samples", C.c_int), ("q1_passes", C.c_int), ("q1_live", C.c_int * 2),
+                ("q1_acc_mask", C.c_int), ("q1_group", C.c_int)]
 
 
 class DecodeArgs(C.Structure):
@@ -140,6 +142,7 @@ def load_library():
     lib.pod_nms_fuse.argtypes = [C.POINTER(NmsArgs), C.c_void_p]
     lib.pod_cluster_merge.argtypes = [C.POINTER(MergeArgs), C.c_void_p]
     lib.pod_wire_records.argtypes = [C.POINTER(WireArgs), C.c_void_p]
+    lib.pod_q1_finish.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 

@@ -56,8 +56,11 @@ def random_state_dict(seed=0, out_channels=256):
     def conv(name, cout, cin, k, bn=True):
         fan = cin * k * k
         sd[name + ".weight"] = torch.randn((cout, cin, k, k), generator=g) * (2.0 / fan) ** 0.5
+        if name.endswith("stem.conv1"):
+            sd[name + ".weight"] /= 64.0            # pixel values are O(100): bring the stem output to O(1)
         if bn:
-            sd[name + ".norm.weight"] = torch.ones(cout)
+            # residual branches start small (as zero-gamma initialisation does) so that 16 stacked blocks keep O(1) maps
+            sd[name + ".norm.weight"] = torch.full((cout,), 0.25) if name.endswith("conv3") else torch.ones(cout)
             sd[name + ".norm.bias"] = torch.zeros(cout)
             sd[name + ".norm.running_mean"] = torch.zeros(cout)
             sd[name + ".norm.running_var"] = torch.ones(cout)

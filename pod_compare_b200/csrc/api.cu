@@ -34,24 +34,26 @@ extern "C" __attribute__((visibility("default"))) int pod_device_ok(void) {
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void k_dropout_mask(uint8_t* keep, int64_t nquads, PhiloxKey key, uint32_t c1, uint32_t sample,
-                               uint32_t image, uint32_t thr) {
-  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nquads; q += (int64_t)gridDim.x * blockDim.x) {
-    const uint4 w = philox4x32_10((uint32_t)q, c1, sample, image, key);
-    uchar4 o;
-    o.x = w.x >= thr; o.y = w.y >= thr; o.z = w.z >= thr; o.w = w.w >= thr;
-    reinterpret_cast<uchar4*>(keep)[q] = o;
+__global__ void k_dropout_mask(uint8_t* keep, int64_t nocts, PhiloxKey key, uint32_t c1, uint32_t sample,
+                               uint32_t image, uint32_t thr16) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nocts; q += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t b = pod_keep8(philox4x32_10((uint32_t)q, c1, sample, image, key), thr16);
+    uchar4 lo4, hi4;
+    lo4.x = b & 1u; lo4.y = (b >> 1) & 1u; lo4.z = (b >> 2) & 1u; lo4.w = (b >> 3) & 1u;
+    hi4.x = (b >> 4) & 1u; hi4.y = (b >> 5) & 1u; hi4.z = (b >> 6) & 1u; hi4.w = (b >> 7) & 1u;
+    reinterpret_cast<uchar4*>(keep)[2 * q] = lo4;
+    reinterpret_cast<uchar4*>(keep)[2 * q + 1] = hi4;
   }
 }
 
 extern "C" __attribute__((visibility("default"))) int pod_philox_dropout_mask(uint8_t* keep_hwc, int H, int W, int C, uint64_t seed, int image, int sample,
                                        int pass, int tower, int layer, int level, double p, void* stream) {
-  POD_REQUIRE(keep_hwc && H > 0 && W > 0 && C > 0 && C % 4 == 0, "pod_philox_dropout_mask: bad shape");
-  const int64_t nq = (int64_t)H * W * C / 4;
+  POD_REQUIRE(keep_hwc && H > 0 && W > 0 && C > 0 && C % 8 == 0, "pod_philox_dropout_mask: bad shape (C%%8)");
+  const int64_t nq = (int64_t)H * W * C / 8;
   const int grid = (int)((nq + 255) / 256 < 4096 ? (nq + 255) / 256 : 4096);
   k_dropout_mask<<<grid, 256, 0, (cudaStream_t)stream>>>(keep_hwc, nq, pod_key(seed, POD_STREAM_DROPOUT),
                                                          pod_dropout_c1(level, layer, tower, pass), (uint32_t)sample,
-                                                         (uint32_t)image, pod_dropout_threshold(p));
+                                                         (uint32_t)image, pod_dropout_threshold16(p));
   POD_LAUNCH_CHECK();
   return 0;
 }

@@ -94,6 +94,23 @@ __host__ __device__ inline uint32_t pod_dropout_threshold(double p) {
   return (uint32_t)t;
 }
 
+// The dropout stream spends 16 random bits per Bernoulli decision: one Philox4x32-10 call serves EIGHT consecutive
+// elements (lane i = bits [16*(i%2), 16*(i%2)+16) of word i/2; keep iff lane >= floor(p * 2^16)).  Half the integer work
+// of a 32-bit-per-decision stream in the two places that evaluate masks for every activation (k_mask_expand, the tower
+// epilogue); the keep probability is (65536 - floor(65536 p)) / 65536, within 1.5e-5 of 1 - p.
+__host__ __device__ inline uint32_t pod_dropout_threshold16(double p) {
+  double t = p * 65536.0;
+  if (t <= 0.0) return 0u;
+  if (t >= 65535.0) return 65535u;
+  return (uint32_t)t;
+}
+// keep bits of the 8 elements served by one call: bit i <-> element 8*c0 + i
+__device__ __forceinline__ uint32_t pod_keep8(const uint4 w, uint32_t thr16) {
+  return ((w.x & 0xFFFFu) >= thr16 ? 1u : 0u) | ((w.x >> 16) >= thr16 ? 2u : 0u) | ((w.y & 0xFFFFu) >= thr16 ? 4u : 0u) |
+         ((w.y >> 16) >= thr16 ? 8u : 0u) | ((w.z & 0xFFFFu) >= thr16 ? 16u : 0u) | ((w.z >> 16) >= thr16 ? 32u : 0u) |
+         ((w.w & 0xFFFFu) >= thr16 ? 64u : 0u) | ((w.w >> 16) >= thr16 ? 128u : 0u);
+}
+
 __host__ __device__ inline uint32_t pod_dropout_c1(int level, int layer, int tower, int pass) {
   return (uint32_t)(level & 0xFF) | ((uint32_t)(layer & 0xFF) << 8) | ((uint32_t)(tower & 0xFF) << 16) |
          ((uint32_t)(pass & 0xFF) << 24);

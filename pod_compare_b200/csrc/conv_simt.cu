@@ -65,13 +65,12 @@ k_conv3x3_simt(const float* __restrict__ in, int H, int W, int Cin, const float*
     }
     if (d.p > 0.0) {
       const int image = d.image0 + n / reps, sample = (n / d.passes) % d.samples, pass = d.pass0 + n % d.passes;
-      const uint32_t q = (uint32_t)(((int64_t)pixel * Cout_pad + c) / 4);
-      const uint4 w = philox4x32_10(q, pod_dropout_c1(d.level, d.layer, d.tower, pass), (uint32_t)sample,
-                                    (uint32_t)image, key);
-      v[0] = w.x >= thr ? v[0] * dscale : 0.f;
-      v[1] = w.y >= thr ? v[1] * dscale : 0.f;
-      v[2] = w.z >= thr ? v[2] * dscale : 0.f;
-      v[3] = w.w >= thr ? v[3] * dscale : 0.f;
+      // 16-bit lanes (common.cuh): one call covers 8 channels; this thread's 4 are its low or high half
+      const int64_t e = (int64_t)pixel * Cout_pad + c;
+      const uint32_t kb = pod_keep8(philox4x32_10((uint32_t)(e >> 3), pod_dropout_c1(d.level, d.layer, d.tower, pass),
+                                                  (uint32_t)sample, (uint32_t)image, key), thr) >> ((e & 4) ? 4 : 0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = ((kb >> j) & 1u) ? v[j] * dscale : 0.f;
     }
     float* o = out + (int64_t)n * out_map_stride + (int64_t)pixel * out_pixel_stride + c;
 #pragma unroll
@@ -94,7 +93,7 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_simt(const flo
   POD_REQUIRE(d.p == 0.0 || Cout == Cout_pad, "pod_conv3x3_simt: dropout needs Cout == Cout_pad");
   dim3 grid(((H + 7) / 8) * ((W + 7) / 8), Cout_pad / TC, NB);
   k_conv3x3_simt<<<grid, 256, 0, (cudaStream_t)stream>>>(in, H, W, Cin, w_kc, bias, Cout, Cout_pad, relu, d,
-                                                         pod_dropout_threshold(d.p), pod_dropout_scale(d.p > 0 ? d.p : 0.5),
+                                                         pod_dropout_threshold16(d.p), pod_dropout_scale(d.p > 0 ? d.p : 0.5),
                                                          pod_key(d.seed, POD_STREAM_DROPOUT), out, out_map_stride,
                                                          out_pixel_stride);
   POD_LAUNCH_CHECK();

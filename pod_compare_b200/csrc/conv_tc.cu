@@ -54,6 +54,7 @@ struct Params {
   int Cout, Cout_pad;
   int relu;
   int dbg_skip_ld;      // debug: skip the TMEM drains (results invalid) to attribute chunk overhead
+  int dbg_no_rmw;       // debug: Q1 accumulation stores without reading back (results invalid) to attribute its cost
   int dbg_fault;        // fault injection (tests): CTA 0's producer never issues its first load -> bounded waits expire
   const float* in_scale_dev;   // optional device-resident input scale (overrides the host value folded into acc_scale)
   const float* out_scale_dev;  // optional device-resident split scale of the HIDDEN output (overrides out_scale)
@@ -72,6 +73,16 @@ struct Params {
   uint32_t drop_thr;
   float drop_scale;
   PhiloxKey key;
+  // Q1 sample accumulation (CTA-pair kernel, last tower layer): see TileRef / tile_ref2 below
+  int q1_mode;          // 0 = plain tile order
+  int q1_samples;       // S: MC samples per image; maps of an image are ordered sample-major, pass-minor
+  int q1_passes;        // tower passes per sample (1 or 2)
+  int q1_live[2];       // samples of pass p that are evaluated at all (S or S - 1, reference quirk Q1)
+  int q1_acc_mask;      // bit p: pass p is ACCUMULATED (weighted sum over its samples) instead of written per sample
+  int q1_group;         // samples per accumulation group (fixed, independent of the batch: bit-reproducible sums)
+  int q1_groups;        // ceil(S / q1_group)
+  int q1_num_pairs;     // unit pairs of the launch
+  float* q1_acc;        // [image][accumulated pass][group][H*W][Cout] fp32 partial sums
 };
 
 // Live-map indirection: the maps of a launch come in groups of `map_group` (one group per image: its samples x
@@ -80,6 +91,69 @@ struct Params {
 __device__ __forceinline__ int physical_map(const Params& P, int m) {
   return P.map_live == P.map_group ? m : (m / P.map_live) * P.map_group + m % P.map_live;
 }
+
+// One unit of work of the CTA-pair kernel.  Plain mode: tile t = 2 * pair + rank.  Q1 mode: the launch is cut into UNITS
+// (image, pass, sample group, pixel tile); a CTA walks the samples of its unit one after the other, so that the epilogue
+// can keep a running weighted sum of the unit's output tile in the (L2-resident) accumulation buffer -- the reference's
+// sample "mean" (2 x0 + x1 + ... + x_{S-2}) / S of probabilistic_inference.py:214-270 commutes with the linear output
+// convolutions cls_score / cls_var / bbox_cov, which are then evaluated ONCE per image on the mean activation
+// instead of once per sample.
+struct TileRef {
+  int n;        // physical input / output map (P.NB: none -- the TMA box is entirely out of bounds and reads zeros)
+  int r;        // pixel tile within the map
+  int ok;       // this CTA has real work in this slot
+  int acc;      // >= 0: accumulate into partial-sum map `acc` (Q1 mode); -1: write the split pair per sample
+  int first;    // first sample of its accumulation group: store instead of add
+  int twice;    // sample 0 enters the reference's sum twice (quirk Q1)
+};
+
+__device__ __forceinline__ int q1_unit_len(const Params& P, int u, int units, int tiles_per_map) {
+  if (u >= units) return 0;
+  const int x = u / tiles_per_map;
+  const int grp = x % P.q1_groups, p = (x / P.q1_groups) % P.q1_passes;
+  const int left = P.q1_live[p] - grp * P.q1_group;
+  return left < 0 ? 0 : (left < P.q1_group ? left : P.q1_group);
+}
+
+// slots (sample steps) the pair spends on unit pair `up`
+__device__ __forceinline__ int pair_len(const Params& P, int up, int tiles_per_map) {
+  if (!P.q1_mode) return 1;
+  const int units = (P.NB / (P.q1_samples * P.q1_passes)) * P.q1_passes * P.q1_groups * tiles_per_map;
+  const int a = q1_unit_len(P, 2 * up, units, tiles_per_map), b = q1_unit_len(P, 2 * up + 1, units, tiles_per_map);
+  return a > b ? a : b;
+}
+
+__device__ __forceinline__ TileRef tile_ref2(const Params& P, int up, int rank, int slot, int tiles_per_map) {
+  TileRef t;
+  t.acc = -1; t.first = 0; t.twice = 0;
+  if (!P.q1_mode) {
+    const int tile = 2 * up + rank;
+    t.ok = tile < P.num_tiles;
+    t.n = t.ok ? physical_map(P, tile / tiles_per_map) : P.NB;
+    t.r = t.ok ? tile % tiles_per_map : 0;
+    return t;
+  }
+  const int images = P.NB / (P.q1_samples * P.q1_passes);
+  const int units = images * P.q1_passes * P.q1_groups * tiles_per_map;
+  const int u = 2 * up + rank;
+  t.ok = slot < q1_unit_len(P, u, units, tiles_per_map);
+  t.n = P.NB; t.r = 0;
+  if (!t.ok) return t;
+  t.r = u % tiles_per_map;
+  int x = u / tiles_per_map;
+  const int grp = x % P.q1_groups; x /= P.q1_groups;
+  const int p = x % P.q1_passes, b = x / P.q1_passes;
+  const int sample = grp * P.q1_group + slot;
+  t.n = (b * P.q1_samples + sample) * P.q1_passes + p;
+  if ((P.q1_acc_mask >> p) & 1) {
+    const int n_acc = __popc(P.q1_acc_mask), a_idx = __popc(P.q1_acc_mask & ((1 << p) - 1));
+    t.acc = (b * n_acc + a_idx) * P.q1_groups + grp;
+    t.first = slot == 0;
+    t.twice = sample == 0;
+  }
+  return t;
+}
+
 
 // ------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -278,7 +352,7 @@ struct CfgH2 {
 template <int NG>
 __device__ __forceinline__ void dropout_bits_slice(const Params& P, int n, int pixel, int col0, int slice, int n_slices,
                                                    uint32_t (&keep)[(NG * 16 + 31) / 32]) {
-  constexpr int CALLS = NG * 4;
+  constexpr int CALLS = NG * 2;                        // one Philox call per 8 columns (16-bit lanes, common.cuh)
   const int per = (CALLS + n_slices - 1) / n_slices;
   const int reps = P.drop.samples * P.drop.passes;
   const uint32_t image = (uint32_t)(P.drop.image0 + n / reps);
@@ -287,16 +361,56 @@ __device__ __forceinline__ void dropout_bits_slice(const Params& P, int n, int p
 #pragma unroll
   for (int q = 0; q < CALLS; ++q) {
     if (q / per == slice) {
-      const uint32_t ctr = (uint32_t)(((long long)pixel * P.Cout_pad + col0 + q * 4) >> 2);
-      const uint4 w = philox4x32_10(ctr, c1, sample, image, P.key);
-      const uint32_t b = (w.x >= P.drop_thr ? 1u : 0u) | (w.y >= P.drop_thr ? 2u : 0u) | (w.z >= P.drop_thr ? 4u : 0u) |
-                         (w.w >= P.drop_thr ? 8u : 0u);
-      keep[q / 8] |= b << ((q % 8) * 4);
+      const uint32_t ctr = (uint32_t)(((long long)pixel * P.Cout_pad + col0 + q * 8) >> 3);
+      keep[q / 4] |= pod_keep8(philox4x32_10(ctr, c1, sample, image, P.key), P.drop_thr) << ((q % 4) * 8);
     }
   }
 }
 
 // bias / ReLU / dropout select / store of one pixel row: NG groups of 16 accumulator columns from `sum`
+// Q1 mode (see TileRef): instead of writing this sample's activation, add it to the running weighted sum of the unit's
+// output tile (fp32, true units).  Two phases so that the L2 round trips overlap: (1) bias / ReLU / dropout in place in
+// the accumulator registers, (2) the 128 partial sums are read back in two batches of sixteen 16-byte loads, added and
+// stored (one batch = one L2 latency; a load issued after a store to the same array cannot be hoisted by the compiler,
+// which made the one-group-at-a-time form pay eight dependent round trips per tile: +12 % on these launches).  The same
+// thread re-reads what it wrote one tile earlier (program order); __ldcg keeps the reads at L2.
+template <int NG>
+__device__ __forceinline__ void tile_epilogue_acc(const Params& P, float (&sum)[NG * 16], int pixel, int col0,
+                                                  const uint32_t (&keep)[(NG * 16 + 31) / 32], int acc_map, int acc_first,
+                                                  int acc_twice) {
+  static_assert(NG == 8, "accumulating epilogue is written for 128 columns per thread");
+  const float acc_scale = P.in_scale_dev != nullptr ? P.acc_scale / __ldg(P.in_scale_dev) : P.acc_scale;
+  const float wgt = acc_twice ? 2.f * P.drop_scale : P.drop_scale;         // dropout scale and the Q1 weight of sample 0
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const uint32_t bits = P.drop_thr != 0u ? keep[g / 2] >> ((g % 2) * 16) : 0xFFFFu;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float v = fmaf(sum[g * 16 + i], acc_scale, __ldg(P.bias + col0 + g * 16 + i));
+      if (P.relu) v = fmaxf(v, 0.f);
+      sum[g * 16 + i] = ((bits >> i) & 1u) ? v * wgt : 0.f;
+    }
+  }
+  float4* q = reinterpret_cast<float4*>(P.q1_acc + ((long long)acc_map * P.H * P.W + pixel) * P.Cout_pad + col0);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float4 o[16];
+    if (!acc_first && !P.dbg_no_rmw) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = __ldcg(q + h * 16 + j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int b = (h * 16 + j) * 4;
+      q[h * 16 + j] = make_float4(__fadd_rn(o[j].x, sum[b]), __fadd_rn(o[j].y, sum[b + 1]), __fadd_rn(o[j].z, sum[b + 2]),
+                                  __fadd_rn(o[j].w, sum[b + 3]));
+    }
+  }
+}
+
 template <int MODE, int NG>
 __device__ __forceinline__ void tile_epilogue(const Params& P, const float (&sum)[NG * 16], int n, int pixel, int col0,
                                               const uint32_t (&keep)[(NG * 16 + 31) / 32]) {
@@ -787,7 +901,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
   const int kb_per_chunk = P.kb_per_chunk;
   const int n_chunks = kb_total / kb_per_chunk;
   const int tiles_per_map = P.tiles_x * P.tiles_y;
-  const int num_pairs = (P.num_tiles + 1) >> 1;
+  const int num_pairs = P.q1_mode ? P.q1_num_pairs : (P.num_tiles + 1) >> 1;
   const int pair0 = (int)cluster_id_x(), pair_step = (int)nclusters_x();
 
   if (warp < 4) {
@@ -798,10 +912,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
     [[maybe_unused]] uint32_t as = 0, aphase = 0;
     bool ok = !(P.dbg_fault && pair0 == 0);            // fault injection: pair 0 never loads -> its waits expire
     for (int tp = pair0; tp < num_pairs && ok; tp += pair_step) {
-      const int tile = 2 * tp + (int)rank;
-      // the odd tail tile of the last pair loads map index NB: entirely out of bounds -> zero fill
-      const int n = tile < P.num_tiles ? physical_map(P, tile / tiles_per_map) : P.NB;
-      const int r = tile < P.num_tiles ? tile % tiles_per_map : 0;
+     const int slots = pair_len(P, tp, tiles_per_map);
+     for (int slot = 0; slot < slots && ok; ++slot) {
+      // a CTA without work in this slot (odd tail, shorter unit) loads map index NB: entirely out of bounds -> zero fill
+      const TileRef tr = tile_ref2(P, tp, (int)rank, slot, tiles_per_map);
+      const int n = tr.n, r = tr.r;
       const int y0 = (r / P.tiles_x) * TILE_H, x0 = (r % P.tiles_x) * TILE_W;
       if constexpr (HALO) {
         for (int cb = 0; cb < kb_per_tap && ok; ++cb) {
@@ -840,6 +955,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
+     }
     }
   } else if (warp == 1 && rank == 0) {
     // ================================ MMA issuer (leader CTA; whole warp, one elected lane issues) ====
@@ -849,6 +965,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
     if constexpr (HALO) {
       uint32_t as = 0, aphase = 0;
       for (int tp = pair0; tp < num_pairs && ok; tp += pair_step) {
+       const int slots = pair_len(P, tp, tiles_per_map);
+       for (int slot = 0; slot < slots && ok; ++slot) {
         int dy = 0;                                     // unit order within a tile: (K-block, dx, dy), dy fastest
         for (int c = 0; c < n_chunks && ok; ++c) {
           if (!mbar_wait_all(&tempty_bar[acc], acc_phase ^ 1u, 12)) { ok = false; break; }
@@ -884,9 +1002,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
           acc ^= 1u;
           if (acc == 0) acc_phase ^= 1u;
         }
+       }
       }
     } else
     for (int tp = pair0; tp < num_pairs && ok; tp += pair_step) {
+     const int slots = pair_len(P, tp, tiles_per_map);
+     for (int slot = 0; slot < slots && ok; ++slot) {
       for (int c = 0; c < n_chunks && ok; ++c) {
         if (!mbar_wait_all(&tempty_bar[acc], acc_phase ^ 1u, 12)) { ok = false; break; }
         tcgen05_fence_after();
@@ -915,6 +1036,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
       }
+     }
     }
   }
   } else {
@@ -927,9 +1049,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
     bool ok = true;
     const uint32_t te0 = mapa_cluster(smem_u32(&tempty_bar[0]), 0), te1 = mapa_cluster(smem_u32(&tempty_bar[1]), 0);
     for (int tp = pair0; tp < num_pairs && ok; tp += pair_step) {
-      const int tile = 2 * tp + (int)rank;
-      const bool tile_ok = tile < P.num_tiles;
-      const int n = tile_ok ? physical_map(P, tile / tiles_per_map) : 0, r = tile_ok ? tile % tiles_per_map : 0;
+     const int slots = pair_len(P, tp, tiles_per_map);
+     for (int slot = 0; slot < slots && ok; ++slot) {
+      const TileRef tr = tile_ref2(P, tp, (int)rank, slot, tiles_per_map);
+      const bool tile_ok = tr.ok != 0;
+      const int n = tile_ok ? tr.n : 0, r = tr.r;
       const int py = (r / P.tiles_x) * TILE_H + m / TILE_W, px = (r % P.tiles_x) * TILE_W + m % TILE_W;
       const bool valid = tile_ok && py < P.H && px < P.W;
       const int pixel = py * P.W + px;
@@ -964,7 +1088,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
         if (MODE == POD_OUT_HIDDEN && P.drop_thr != 0u && valid) dropout_bits_slice<NG>(P, n, pixel, col0, c, n_chunks, keep);
       }
       if (!ok || !valid) continue;
-      tile_epilogue<MODE, NG>(P, sum, n, pixel, col0, keep);
+      if (MODE == POD_OUT_HIDDEN && tr.acc >= 0) tile_epilogue_acc<NG>(P, sum, pixel, col0, keep, tr.acc, tr.first, tr.twice);
+      else tile_epilogue<MODE, NG>(P, sum, n, pixel, col0, keep);
+     }
     }
   }
 
@@ -1047,7 +1173,7 @@ static int launch2(const Params& P, cudaStream_t st) {
     POD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  const int pairs = (P.num_tiles + 1) / 2;
+  const int pairs = P.q1_mode ? P.q1_num_pairs : (P.num_tiles + 1) / 2;
   const int max_pairs = pod_num_sms() / 2;
   const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
   kern<<<grid, NUM_THREADS, SMEM, st>>>(P);
@@ -1514,6 +1640,7 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   P.kb_per_chunk = g_tc_taps * (a->Cin / BK);
   if (g_tc_chunk_kb > 0 && (9 * (a->Cin / BK)) % g_tc_chunk_kb == 0) P.kb_per_chunk = g_tc_chunk_kb;
   P.dbg_skip_ld = getenv("POD_TC_DEBUG_SKIP_LD") ? 1 : 0;
+  P.dbg_no_rmw = getenv("POD_TC_DEBUG_NO_RMW") ? 1 : 0;
   P.dbg_fault = g_tc_fault;
   P.in_scale_dev = a->in_scale_dev;
   P.acc_scale = 1.0f / ((a->in_scale_dev ? 1.0f : a->in_scale) * a->w_scale) *
@@ -1538,7 +1665,8 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
     POD_REQUIRE(((uintptr_t)a->out_hi | (uintptr_t)a->out_lo) % 16 == 0, "pod_conv3x3_tc: outputs must be 16-byte aligned");
     if (a->drop.p > 0.0) {
       POD_REQUIRE(a->drop.p < 1.0, "pod_conv3x3_tc: dropout p must be < 1");
-      P.drop_thr = pod_dropout_threshold(a->drop.p);
+      P.drop_thr = pod_dropout_threshold16(a->drop.p);
+      if (P.drop_thr == 0u) P.drop_thr = 1u;           // p < 2^-16: keep (almost) everything, but stay in dropout mode
       P.drop_scale = pod_dropout_scale(a->drop.p);
       P.key = pod_key(a->drop.seed, POD_STREAM_DROPOUT);
     }
@@ -1553,6 +1681,28 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
     }
   } else {
     POD_REQUIRE(false, "pod_conv3x3_tc: unknown mode %d", a->mode);
+  }
+  if (a->q1_acc != nullptr) {
+    // Q1 sample accumulation (see TileRef): last tower layer of an MC-dropout head, CTA-pair kernel only
+    POD_REQUIRE(a->mode == POD_OUT_HIDDEN && a->Cout_pad == 256 && tc::g_tc_pair, "pod_conv3x3_tc: q1_acc needs a 256-channel hidden "
+                "convolution on the CTA-pair kernel");
+    POD_REQUIRE(a->q1_samples > 1 && (a->q1_passes == 1 || a->q1_passes == 2) && a->NB % (a->q1_samples * a->q1_passes) == 0,
+                "pod_conv3x3_tc: q1 maps must come as images x samples x passes");
+    POD_REQUIRE(a->q1_group > 0 && a->q1_acc_mask > 0 && a->q1_acc_mask < (1 << a->q1_passes), "pod_conv3x3_tc: bad q1 group / pass mask");
+    POD_REQUIRE(a->q1_live[0] >= 0 && a->q1_live[0] <= a->q1_samples && a->q1_live[1] >= 0 && a->q1_live[1] <= a->q1_samples,
+                "pod_conv3x3_tc: q1_live out of range");
+    POD_REQUIRE((uintptr_t)a->q1_acc % 16 == 0, "pod_conv3x3_tc: q1_acc must be 16-byte aligned");
+    POD_REQUIRE(a->map_group == 0 || a->map_group == a->q1_samples * a->q1_passes, "pod_conv3x3_tc: q1 and map_group disagree");
+    P.q1_mode = 1;
+    P.q1_samples = a->q1_samples; P.q1_passes = a->q1_passes;
+    P.q1_live[0] = a->q1_live[0]; P.q1_live[1] = a->q1_passes > 1 ? a->q1_live[1] : 0;
+    P.q1_acc_mask = a->q1_acc_mask;
+    P.q1_group = a->q1_group;
+    P.q1_groups = (a->q1_samples + a->q1_group - 1) / a->q1_group;
+    P.q1_acc = a->q1_acc;
+    const long long units = (long long)(a->NB / (a->q1_samples * a->q1_passes)) * a->q1_passes * P.q1_groups * P.tiles_x * P.tiles_y;
+    POD_REQUIRE(units < (1ll << 30), "pod_conv3x3_tc: too many q1 units");
+    P.q1_num_pairs = (int)((units + 1) / 2);
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (halo) {

@@ -181,7 +181,7 @@ extern "C" __attribute__((visibility("default"))) int pod_pack_conv_weight_f32(c
 // ---------------------------------------------------------------------------------------------
 // MC-dropout replication of the first tower layer: one read, samples*passes masked split copies
 // ---------------------------------------------------------------------------------------------
-// one thread = 8 consecutive channels (two Philox quads): 32-byte loads, 16-byte stores per copy
+// one thread = 8 consecutive channels (one Philox call, 16-bit lanes): 32-byte loads, 16-byte stores per copy
 __global__ void __launch_bounds__(256)
 k_mask_expand(const float* __restrict__ x, int64_t oct_per_map, int NB_in, pod_dropout d, float scale, const float* __restrict__ scale_dev,
               uint32_t thr, float dscale, PhiloxKey key, __half* __restrict__ hi, __half* __restrict__ lo, int live_reps) {
@@ -212,13 +212,12 @@ k_mask_expand(const float* __restrict__ x, int64_t oct_per_map, int NB_in, pod_d
     for (int r = 0; r < live_reps; ++r) {
       const int sample = r / d.passes, pass = d.pass0 + r % d.passes;
       const uint32_t c1 = pod_dropout_c1(d.level, d.layer, d.tower, pass);
-      const uint4 wa = philox4x32_10((uint32_t)(2 * o8), c1, (uint32_t)sample, image, key);
-      const uint4 wb = philox4x32_10((uint32_t)(2 * o8 + 1), c1, (uint32_t)sample, image, key);
-      const uint32_t w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+      // one call serves this thread's 8 channels (16-bit lanes, common.cuh)
+      const uint32_t kb = pod_keep8(philox4x32_10((uint32_t)o8, c1, (uint32_t)sample, image, key), thr);
       uint32_t ph[4], pl[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const uint32_t m = (w[2 * i] >= thr ? 0x0000FFFFu : 0u) | (w[2 * i + 1] >= thr ? 0xFFFF0000u : 0u);
+        const uint32_t m = ((kb >> (2 * i)) & 1u ? 0x0000FFFFu : 0u) | ((kb >> (2 * i + 1)) & 1u ? 0xFFFF0000u : 0u);
         ph[i] = kh[i] & m;
         pl[i] = kl[i] & m;
       }
@@ -239,9 +238,57 @@ extern "C" __attribute__((visibility("default"))) int pod_mask_expand_split(cons
   const int64_t total = qpm * NB_in;
   // 39 registers x 256 threads: six CTAs are resident per SM; a grid of exactly that many leaves no partial last wave
   const int grid = (int)((total + 255) / 256 < (int64_t)pod_num_sms() * 6 ? (total + 255) / 256 : (int64_t)pod_num_sms() * 6);
-  k_mask_expand<<<grid, 256, 0, (cudaStream_t)stream>>>(x, qpm, NB_in, *d, scale, scale_dev, pod_dropout_threshold(d->p),
+  k_mask_expand<<<grid, 256, 0, (cudaStream_t)stream>>>(x, qpm, NB_in, *d, scale, scale_dev, pod_dropout_threshold16(d->p),
                                                         pod_dropout_scale(d->p), pod_key(d->seed, POD_STREAM_DROPOUT),
                                                         (__half*)dst_hi, (__half*)dst_lo, live_reps);
+  POD_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Q1 sample accumulation, second half: partial sums of the last tower layer (written by the tcgen05 epilogue,
+// pod_conv_args.q1_acc) -> mean activation as fp16 split pair.  8 channels per thread.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_q1_finish(const float* __restrict__ acc, int64_t oct_per_map, int64_t total, int groups, float inv_div, float scale,
+            const float* __restrict__ scale_dev, __half* __restrict__ hi, __half* __restrict__ lo) {
+  if (scale_dev != nullptr) scale = __ldg(scale_dev);
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = t / oct_per_map, o8 = t % oct_per_map;
+    const float4* p = reinterpret_cast<const float4*>(acc) + (m * groups * oct_per_map + o8) * 2;
+    float4 a0 = __ldcs(p), a1 = __ldcs(p + 1);
+    for (int g = 1; g < groups; ++g) {
+      const float4 b0 = __ldcs(p + (int64_t)g * oct_per_map * 2), b1 = __ldcs(p + (int64_t)g * oct_per_map * 2 + 1);
+      a0 = make_float4(__fadd_rn(a0.x, b0.x), __fadd_rn(a0.y, b0.y), __fadd_rn(a0.z, b0.z), __fadd_rn(a0.w, b0.w));
+      a1 = make_float4(__fadd_rn(a1.x, b1.x), __fadd_rn(a1.y, b1.y), __fadd_rn(a1.z, b1.z), __fadd_rn(a1.w, b1.w));
+    }
+    const float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    uint32_t ph[4], pl[4];
+    bool saturated = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float x0 = __fdiv_rn(v[2 * i], inv_div) * scale, x1 = __fdiv_rn(v[2 * i + 1], inv_div) * scale;
+      saturated |= !(fabsf(x0) <= 65504.f) | !(fabsf(x1) <= 65504.f);
+      __half h0, l0, h1, l1;
+      pod_split_h(x0, h0, l0);
+      pod_split_h(x1, h1, l1);
+      ph[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      pl[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    if (saturated) atomicCAS(&g_prep_status, 0, 101);
+    reinterpret_cast<uint4*>(hi)[t] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    reinterpret_cast<uint4*>(lo)[t] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+}
+
+extern "C" __attribute__((visibility("default"))) int pod_q1_finish(const float* acc, int n_maps, int groups, int64_t n, int samples, float scale,
+                                                      const float* scale_dev, void* dst_hi, void* dst_lo, void* stream) {
+  POD_REQUIRE(acc && dst_hi && dst_lo && n_maps > 0 && groups > 0 && n > 0 && n % 8 == 0 && samples > 0, "pod_q1_finish: bad args (n%%8)");
+  POD_REQUIRE(((uintptr_t)acc | (uintptr_t)dst_hi | (uintptr_t)dst_lo) % 16 == 0, "pod_q1_finish: buffers must be 16-byte aligned");
+  const int64_t opm = n / 8, total = opm * n_maps;
+  const int64_t want = (total + 255) / 256, cap = (int64_t)pod_num_sms() * 8;
+  k_q1_finish<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(acc, opm, total, groups, (float)samples, scale, scale_dev,
+                                                                               (__half*)dst_hi, (__half*)dst_lo);
   POD_LAUNCH_CHECK();
   return 0;
 }

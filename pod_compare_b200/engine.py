@@ -30,6 +30,8 @@ ACT_SCALE = 16.0          # largest fp16 split scale of activations (|x| < 4094,
 FEATURE_TARGET = 128.0    # = 8 * ACT_SCALE: stored features stay below 128, leaving 512x headroom (65504 / 128) for hidden
                           # activations larger than the features; beyond that pod_status reports saturation
 TOWER_CLS, TOWER_BOX = 0, 1
+Q1_GROUP = 8              # samples per partial sum of the fused Q1 accumulation: fixed, so the fp32 summation order (and
+                          # with it every bit of the result) does not depend on the batch size or the GPU count
 
 
 def _pad_cout(c):
@@ -169,9 +171,19 @@ class HeadEngine:
                            in_map_stride=in_map_stride, in_offset=in_offset, map_group=map_group, map_live=map_live,
                            in_scale_dev=scale_dev)
 
-    def head_mc(self, feats, n_mc, seed, image0, skip_unread=False):
+    def head_mc(self, feats, n_mc, seed, image0, skip_unread=False, fuse_q1=False):
         """MC-dropout head loop: feats = list over levels of (B,256,H,W) fp32.
         Returns raw per-sample outputs, each (B, N, R, D).
+
+        fuse_q1 (pre-NMS aggregation only, implies skip_unread): the reference's sample "mean" of box_cls, box_cls_var
+        and box_reg_var (probabilistic_inference.py:214-270) is a fixed linear combination of the samples, and cls_score /
+        cls_var / bbox_cov are linear (a 3x3 convolution plus bias; the weights sum to one), so
+            mean_s head(x_s) = head(mean_s x_s).
+        The last tower layer then accumulates (2 x_0 + x_1 + ... + x_{N-2}) in its epilogue instead of writing N maps,
+        and each of those three output convolutions runs ONCE per image: 3 + N output convolutions per location instead
+        of 4N - 3, and no per-sample logits / variances are ever written (returned with a sample dimension of 1: they
+        ARE the Q1 means).  Only box_delta stays per sample: every sample's decoded box enters the epistemic
+        covariance (:326-331).  Differs from the unfused evaluation by fp32 round-off (~1e-7 relative).
 
         skip_unread: the reference's sample "mean" of box_cls / box_cls_var / box_reg_var runs over
         range(len-1) (probabilistic_inference.py:216-267), so those three outputs of the LAST sample are
@@ -190,11 +202,19 @@ class HeadEngine:
         R = level_off[-1]
         passes = 2 if (pc.cls_var or pc.bbox_cov) else 1
         dev = self.device
-        raw = {"logits": torch.empty((B, n_mc, R, K), dtype=torch.float32, device=dev),
+        fuse = bool(fuse_q1) and n_mc > 1
+        if fuse:
+            skip_unread = True
+        n_stat = 1 if fuse else n_mc                     # sample dimension of the outputs that are only ever averaged
+        raw = {"logits": torch.empty((B, n_stat, R, K), dtype=torch.float32, device=dev),
                "deltas": torch.empty((B, n_mc, R, 4), dtype=torch.float32, device=dev),
-               "logvar": torch.empty((B, n_mc, R, K), dtype=torch.float32, device=dev) if pc.cls_var else None,
-               "regvar": torch.empty((B, n_mc, R, pc.cov_dims), dtype=torch.float32, device=dev) if pc.bbox_cov else None}
+               "logvar": torch.empty((B, n_stat, R, K), dtype=torch.float32, device=dev) if pc.cls_var else None,
+               "regvar": torch.empty((B, n_stat, R, pc.cov_dims), dtype=torch.float32, device=dev) if pc.bbox_cov else None}
         max_hw = max(h * wd for h, wd in level_hw)
+        groups = (n_mc + Q1_GROUP - 1) // Q1_GROUP
+        if fuse:
+            q1_acc = self._get("q1_acc", B * 2 * groups * max_hw * 256, torch.float32)
+            q1_mean = (self._get("q1m_hi", B * 2 * max_hw * 256, torch.float16), self._get("q1m_lo", B * 2 * max_hw * 256, torch.float16))
         nmaps = B * n_mc * passes
         act = [(self._get("a%d_hi" % i, nmaps * max_hw * 256, torch.float16),
                 self._get("a%d_lo" % i, nmaps * max_hw * 256, torch.float16)) for i in range(2)]
@@ -223,15 +243,47 @@ class HeadEngine:
                                       scale_dev=fscale)
                 cur = 0
                 NB = B * n_mc * t_passes
+                # passes of this tower whose last layer is only ever averaged over the samples (fused Q1 accumulation)
+                acc_mask = 0
+                if fuse:
+                    acc_mask = ((1 << t_passes) - 1) if tower == TOWER_CLS else (2 if has_var else 0)
+                n_acc = bin(acc_mask).count("1")
                 for layer in range(1, len(tw)):
                     d = ops.make_dropout(pc.dropout_rate, seed, image0, n_mc, t_passes, 0, tower, layer, lvl)
-                    self._conv_hidden(act[cur], NB, H, W, tw[layer], act[cur ^ 1], d, fscale, map_group=grp, map_live=live)
+                    if acc_mask and layer == len(tw) - 1:
+                        q1_live = [n_mc - 1, n_mc - 1] if tower == TOWER_CLS else [n_mc, n_mc - 1]
+                        ops.conv3x3_tc(act[cur][0], act[cur][1], 1.0, NB, H, W, 256, tw[layer].w_hi, tw[layer].w_lo,
+                                       tw[layer].w_scale, tw[layer].bias, 256, 256, POD_OUT_HIDDEN, True,
+                                       out_hi=act[cur ^ 1][0], out_lo=act[cur ^ 1][1], out_scale=1.0, drop=d,
+                                       in_scale_dev=fscale, out_scale_dev=fscale,
+                                       q1={"acc": q1_acc, "samples": n_mc, "passes": t_passes, "live": q1_live[:t_passes],
+                                           "mask": acc_mask, "group": Q1_GROUP})
+                        ops.q1_finish(q1_acc, B * n_acc, groups, HW * 256, n_mc, fscale, q1_mean[0], q1_mean[1])
+                    else:
+                        self._conv_hidden(act[cur], NB, H, W, tw[layer], act[cur ^ 1], d, fscale, map_group=grp, map_live=live)
                     cur ^= 1
                 n_live = n_mc - 1 if (skip_unread and n_mc > 1) else n_mc        # samples whose mean/var heads are read
                 # output convs: pass-0 maps feed the mean head, pass-1 maps the variance head (Q2)
                 mean_pc, var_pc = (w.cls_score, w.cls_var) if tower == TOWER_CLS else (w.bbox_pred, w.bbox_cov)
                 mean_out = raw["logits"] if tower == TOWER_CLS else raw["deltas"]
                 D = mean_pc[0].total_cout // A
+                if acc_mask:
+                    # the averaged outputs: ONE convolution per image on the mean activation (accumulated pass a of image b
+                    # is map b * n_acc + a of q1_mean)
+                    a_idx = 0
+                    if tower == TOWER_CLS:
+                        self._conv_out(q1_mean, B, H, W, mean_pc, mean_out, level_off[lvl] * D, R * D, fscale,
+                                       in_map_stride=n_acc * HW * 256, in_offset=0)
+                        a_idx = 1
+                    else:
+                        self._conv_out(act[cur], B * n_mc, H, W, mean_pc, mean_out, level_off[lvl] * D, R * D, fscale,
+                                       in_map_stride=t_passes * HW * 256, in_offset=0, map_group=n_mc, map_live=n_mc)
+                    if has_var:
+                        var_out = raw["logvar"] if tower == TOWER_CLS else raw["regvar"]
+                        Dv = var_pc[0].total_cout // A
+                        self._conv_out(q1_mean, B, H, W, var_pc, var_out, level_off[lvl] * Dv, R * Dv, fscale,
+                                       in_map_stride=n_acc * HW * 256, in_offset=a_idx * HW * 256)
+                    continue
                 self._conv_out(act[cur], B * n_mc, H, W, mean_pc, mean_out, level_off[lvl] * D, R * D, fscale,
                                in_map_stride=t_passes * HW * 256, in_offset=0, map_group=n_mc,
                                map_live=n_live if tower == TOWER_CLS else n_mc)
@@ -323,12 +375,13 @@ class HeadEngine:
         if runs > 1:
             raw = {k: (v.reshape((v.shape[0] * v.shape[1], 1) + tuple(v.shape[2:])) if v is not None else None)
                    for k, v in raw.items()}
-        S = raw["logits"].shape[1]
+        S = raw["deltas"].shape[1]
         if S > 1:
-            m_logits = ops.sample_mean_q1(raw["logits"])
-            m_deltas = ops.sample_mean_q1(raw["deltas"])
-            m_logvar = ops.sample_mean_q1(raw["logvar"]) if raw["logvar"] is not None else None
-            m_regvar = ops.sample_mean_q1(raw["regvar"]) if raw["regvar"] is not None else None
+            # outputs that arrive with a sample dimension of 1 already ARE the Q1 means (head_mc fuse_q1)
+            q1 = lambda t: None if t is None else (ops.sample_mean_q1(t) if t.shape[1] > 1 else
+                                                   (t[:, 0] if t.shape[0] == 1 else t[:, 0].contiguous()))
+            m_logits, m_deltas = q1(raw["logits"]), ops.sample_mean_q1(raw["deltas"])
+            m_logvar, m_regvar = q1(raw["logvar"]), q1(raw["regvar"])
         else:
             m_logits, m_deltas = raw["logits"][:, 0], raw["deltas"][:, 0]
             m_logvar = raw["logvar"][:, 0] if raw["logvar"] is not None else None

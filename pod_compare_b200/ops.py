@@ -173,7 +173,8 @@ def mask_expand_split(x, drop, scale, out_hi=None, out_lo=None, live_reps=0, sca
 def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias, Cout, Cout_pad, mode, relu,
                out_hi=None, out_lo=None, out_scale=1.0, out_f32=None, out_map_stride=0, out_pixel_stride=0,
                drop=None, in_map_stride=None, in_offset=0, out_offset=0, out2_f32=None, out2_offset=0, split_col=0,
-               out2_map_stride=0, out2_pixel_stride=0, map_group=0, map_live=0, in_scale_dev=None, out_scale_dev=None):
+               out2_map_stride=0, out2_pixel_stride=0, map_group=0, map_live=0, in_scale_dev=None, out_scale_dev=None,
+               q1=None):
     """Raw-pointer launch of the tcgen05 convolution. `in_offset`/`out_offset` are ELEMENT offsets
     into in_hi/in_lo and out_f32.  in_scale_dev: 1-element fp32 CUDA tensor replacing in_scale."""
     lib = _cabi.require_device()
@@ -199,6 +200,12 @@ def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias,
     a.map_group, a.map_live = int(map_group), int(map_live)
     a.in_scale_dev = in_scale_dev.data_ptr() if in_scale_dev is not None else None
     a.out_scale_dev = out_scale_dev.data_ptr() if out_scale_dev is not None else None
+    if q1 is not None:
+        # Q1 sample accumulation of the last tower layer (include/podb200.h, pod_conv_args.q1_acc)
+        a.q1_acc = q1["acc"].data_ptr()
+        a.q1_samples, a.q1_passes = int(q1["samples"]), int(q1["passes"])
+        a.q1_live[0], a.q1_live[1] = int(q1["live"][0]), int(q1["live"][1] if len(q1["live"]) > 1 else 0)
+        a.q1_acc_mask, a.q1_group = int(q1["mask"]), int(q1["group"])
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -206,7 +213,11 @@ def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias,
     if PROFILE is not None:
         e1.record()
         tag = "tower256" if (Cout_pad == 256 and mode == POD_OUT_HIDDEN) else ("conv1" if Cout_pad == 256 else "out")
+        if q1 is not None:
+            tag = "tower256_q1"
         maps = NB if not map_group else NB // map_group * map_live          # maps actually evaluated
+        if q1 is not None:
+            maps = NB // (a.q1_samples * a.q1_passes) * sum(int(v) for v in q1["live"][:a.q1_passes])
         PROFILE.append((e0, e1, 2.0 * 9 * Cin * Cout * maps * H * W, tag))
     _count()
 
@@ -491,3 +502,13 @@ def wire_records(det, xywh=False, cat_map=None, out=None):
     check(lib.pod_wire_records(C.byref(a), stream_ptr()), "pod_wire_records")
     _count()
     return out
+
+
+def q1_finish(acc, n_maps, groups, n, samples, scale_dev, out_hi, out_lo):
+    """Partial sample sums of the last tower layer -> mean activation maps as fp16 split pair (pod_q1_finish)."""
+    lib = _cabi.require_device()
+    _chk(acc, torch.float32, "acc")
+    assert acc.numel() >= n_maps * groups * n and out_hi.numel() >= n_maps * n and out_lo.numel() >= n_maps * n
+    check(lib.pod_q1_finish(ptr(acc), int(n_maps), int(groups), int(n), int(samples), 1.0, ptr(scale_dev), ptr(out_hi), ptr(out_lo),
+                            stream_ptr()), "pod_q1_finish")
+    _count()

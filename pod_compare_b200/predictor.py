@@ -81,6 +81,11 @@ class ProbabilisticPredictor:
         # (reference probabilistic_inference.py:216-267 loops over range(len-1)): the tower passes feeding
         # only those outputs are left out.  Results are unchanged; set False to evaluate them anyway.
         self.skip_unread_outputs = True
+        # Pre-NMS MC-dropout aggregation: the sample "mean" of box_cls / box_cls_var / box_reg_var commutes with the linear
+        # output convolutions, so the last tower layer accumulates the reference's weighted sample sum in its epilogue and
+        # cls_score / cls_var / bbox_cov run once per image (engine.HeadEngine.head_mc fuse_q1).  Needs skip_unread_outputs;
+        # set False to evaluate and average every sample's outputs as the reference does.
+        self.fuse_sample_mean = True
         self.max_activation_bytes = 64e9  # auto-chunking budget of infer_from_features / predict_batch
         self._copy_stream = None          # host->device prefetch of the next chunk (infer_from_features chunk_images)
         self.rng_seed = int(self.cfg.SEED) if int(self.cfg.SEED) >= 0 else 0
@@ -263,8 +268,9 @@ class ProbabilisticPredictor:
             # NUM_RUNS == 1 keeps the reference's behaviour too: the model stays in train mode (:52-56), so the single
             # forward has active dropout and the mean / variance heads see independently masked tower passes (Q2)
             n_runs = max(1, int(self.num_mc_dropout_runs))
-            raw, level_off = eng.head_mc(feats, n_runs, seed, image0,
-                                         skip_unread=self.skip_unread_outputs and not post_nms and n_runs > 1)
+            skip = self.skip_unread_outputs and not post_nms and n_runs > 1
+            raw, level_off = eng.head_mc(feats, n_runs, seed, image0, skip_unread=skip,
+                                         fuse_q1=skip and self.fuse_sample_mean and not return_raw)
         elif self.mc_dropout_enabled and self.num_mc_dropout_runs > 1:
             raise _cabi.PodError("MC_DROPOUT.ENABLE with DROPOUT_RATE == 0 is not supported")
         else:

@@ -98,6 +98,21 @@ def make_head_state_dict(seed, num_classes=7, num_anchors=9, channels=256, num_c
     return sd
 
 
+def make_member_state_dicts(members, correlation=0.95, **kw):
+    """E weight sets that behave like members of a trained ensemble: independently initialised networks trained on the
+    same data agree on most predictions, so the members share a common component (correlation) plus a member-specific
+    one.  Fully independent random heads (make_head_state_dict(1000 * e)) average their logits to nothing: with the
+    reference's Q1 mean over 5 such members no anchor passes SCORE_THRESH_TEST and the post-processing would run on
+    empty candidate lists.  Biases keep their (deterministic) values."""
+    base = make_head_state_dict(0, **kw)
+    own_w = math.sqrt(1.0 - correlation * correlation)
+    out = []
+    for e in range(members):
+        own = make_head_state_dict(1000 * (e + 1), **kw)
+        out.append({k: ((correlation * base[k] + own_w * own[k]) if k.endswith(".weight") else base[k].clone()) for k in base})
+    return out
+
+
 def make_image(seed, image_idx, height=720, width=1280):
     g = torch.Generator().manual_seed(1234 + 7919 * int(seed) + int(image_idx))
     return torch.randint(0, 256, (3, height, width), generator=g, dtype=torch.uint8)
