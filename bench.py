@@ -264,6 +264,7 @@ def main():
     ap.add_argument("--no-fuse-q1", action="store_true",
                     help="evaluate cls_score / cls_var / bbox_cov for every MC sample and average the outputs (as the reference "
                          "does) instead of accumulating the last tower layer over the samples (default: fused)")
+    ap.add_argument("--profile-layers", action="store_true", help="report tower time per layer in ms_per_step_by_kernel")
     ap.add_argument("--halo", type=int, default=-1, help="row-halo activation staging: bit 0 = pixels-as-M kernels, bit 1 = weights-as-A kernel (default 3)")
     ap.add_argument("--chunk-taps", type=int, default=0, help="taps per accumulation chunk (1, 3, 9)")
     ap.add_argument("--chunk-kblocks", type=int, default=0, help="K-blocks per accumulation chunk (overrides --chunk-taps)")
@@ -304,6 +305,7 @@ def main():
     pred.load_weight_sets(sds if members > 1 else sds[0])
     pred.skip_unread_outputs = not args.keep_unread
     pred.fuse_sample_mean = not args.no_fuse_q1
+    pred._engine.profile_layers = args.profile_layers
     B = args.batch
     # synthetic FPN features of this rank's images (weak scaling: B images per GPU)
     img0 = rank * B
@@ -410,7 +412,7 @@ def main():
                 h[0] += d; h[1] += flop; h[2] += 1
                 continue
             all_ms += d
-            if tag in ("tower256", "tower256_q1"):
+            if tag.startswith("tower256"):
                 tot_ms += d
                 tot_flop += flop
                 n += 1

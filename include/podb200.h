@@ -205,6 +205,59 @@ int pod_conv3x3_tc_status(int* status_host);
 int pod_conv3x3_tc_set_wait_limit(long long cycles);
 int pod_conv3x3_tc_debug_fault(int on);
 
+/* ---- general convolution for the ResNet-50-FPN backbone (detectron2 build_retinanet_resnet_fpn_backbone,
+ *      call sites probabilistic_retinanet.py:96-101) -------------------------------------------------------------------
+ * 1x1 or 3x3 (padding ksize/2), stride 1 or 2, channels-last fp16 split pair in, on the same tcgen05 implicit-GEMM
+ * kernel as the head (fp16x3 split operands, fp32 TMEM accumulation, chunked K loop).  FrozenBatchNorm is folded into
+ * the packed weights (scale) and `bias`.  One launch evaluates ONE column block of block_cols (64 / 128 / 256) output
+ * channels starting at col0 of a weight matrix packed by pod_pack_conv_weight_k with Cout_rows rows.
+ *   out_hi/out_lo : (NB, Hout, Wout, out_ch_stride) split pair scaled by out_scale; this block writes channels
+ *                   [col0, col0 + block_cols);  y = relu?(conv + bias (+ residual))
+ *   res_hi/res_lo : optional residual with the layout of the output (bottleneck shortcut), scaled by res_scale
+ *   out_f32       : alternative fp32 channels-last output (NB, Hout, Wout, out_ch_stride) -- the FPN maps handed to the head */
+typedef struct pod_convg_args {
+  const void* in_hi;
+  const void* in_lo;
+  float in_scale;
+  int NB, Hin, Win, Cin;
+  int ksize, stride;
+  int Hout, Wout;
+  const void* w_hi;
+  const void* w_lo;
+  float w_scale;
+  int Cout_rows;          /* rows of the packed weight matrix (multiple of block_cols) */
+  int Cout;               /* real output channels */
+  int col0, block_cols;
+  const float* bias;      /* Cout_rows fp32 */
+  int relu;
+  void* out_hi;
+  void* out_lo;
+  float out_scale;
+  int out_ch_stride;
+  const void* res_hi;
+  const void* res_lo;
+  float res_scale;
+  float* out_f32;
+} pod_convg_args;
+int pod_conv_tc_general(const pod_convg_args* a, void* stream);
+/* nn.Conv2d weight (Cout, Cin, k, k) -> K-major rows [Cout_pad][k*k*Cin], column (ky*k+kx)*Cin + ci, fp16 split pair. */
+int pod_pack_conv_weight_k(const float* w_oihw, int Cout, int Cin, int ksize, int Cout_pad, float scale,
+                           void* dst_hi, void* dst_lo, void* stream);
+/* Stem of the ResNet: (image - mean) / std, zero-padded from (Himg, Wimg) to the size-divisible (H, W) (detectron2
+ * preprocess_image: ImageList.from_tensors pads the NORMALISED image with zeros) -> 7x7 / stride 2 / pad 3 convolution
+ * 3 -> 64 (+ folded FrozenBN, ReLU) -> 3x3 / stride 2 / pad 1 max-pool, SIMT fp32.  images (NB, 3, Himg, Wimg) uint8
+ * (is_u8) or fp32; w [(ky*7+kx)*3+c][64] with the BN scale folded in, bias 64.  out: (NB, Hp, Wp, 64) split pair,
+ * Hp = ceil(ceil(H/2)/2). */
+int pod_stem_conv7_pool(const void* images_nchw, int is_u8, int NB, int Himg, int Wimg, int H, int W,
+                        const float* mean3_host, const float* std3_host, const float* w147x64, const float* bias,
+                        float* scratch /* NB*Hc*Wc*64 fp32, Hc = ceil(H/2) */, void* out_hi, void* out_lo, float out_scale,
+                        void* stream);
+/* FPN top-down step on fp32 channels-last maps: dst (NB,H,W,C) += nearest-upsample-by-2 of src (NB,ceil(H/2),ceil(W/2),C). */
+int pod_upsample2_add(float* dst, const float* src, int NB, int H, int W, int C, void* stream);
+/* fp32 channels-last -> fp16 split pair with a device-resident scale (FPN maps -> head operand), optional ReLU first. */
+int pod_split_f32(const float* src, int64_t n, float scale, const float* scale_dev, int relu, void* dst_hi, void* dst_lo,
+                  void* stream);
+
 /* Plain fp32 SIMT convolution with the same semantics (cross-check of the tensor-core kernel;
  * not on the product path). in (NB,H,W,Cin) fp32, w from pod_pack_conv_weight_f32. */
 int pod_conv3x3_simt(const float* in, int NB, int H, int W, int Cin, const float* w_kc, const float* bias,

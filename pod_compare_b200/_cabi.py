@@ -18,6 +18,7 @@ EXPORTS = [
     "pod_mask_expand_split", "pod_conv3x3_tc", "pod_conv3x3_tc_set_kblock", "pod_conv3x3_tc_set_chunk_taps", "pod_conv3x3_tc_set_chunk_kblocks", "pod_conv3x3_tc_set_pair", "pod_conv3x3_tc_set_halo", "pod_conv3x3_tc_set_wt", "pod_conv3x3_tc_set_trunc_comp", "pod_conv3x3_tc_status",
     "pod_conv3x3_simt", "pod_sample_mean_q1", "pod_scores", "pod_topk_levels", "pod_decode_cov", "pod_nms_fuse",
     "pod_cluster_merge", "pod_wire_records", "pod_q1_finish",
+    "pod_conv_tc_general", "pod_pack_conv_weight_k", "pod_stem_conv7_pool", "pod_upsample2_add", "pod_split_f32",
 ]
 
 POD_OUT_HIDDEN, POD_OUT_RAW = 0, 1
@@ -74,6 +75,16 @@ class MergeArgs(C.Structure):
                 ("det_count", C.c_void_p), ("B", C.c_int), ("runs", C.c_int), ("max_dets", C.c_int), ("K", C.c_int),
                 ("affinity", C.c_double), ("out_boxes", C.c_void_p), ("out_cov", C.c_void_p), ("out_scores", C.c_void_p),
                 ("out_classes", C.c_void_p), ("out_probs", C.c_void_p), ("out_count", C.c_void_p)]
+
+
+class ConvGArgs(C.Structure):
+    _fields_ = [("in_hi", C.c_void_p), ("in_lo", C.c_void_p), ("in_scale", C.c_float),
+                ("NB", C.c_int), ("Hin", C.c_int), ("Win", C.c_int), ("Cin", C.c_int), ("ksize", C.c_int), ("stride", C.c_int),
+                ("Hout", C.c_int), ("Wout", C.c_int), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("w_scale", C.c_float),
+                ("Cout_rows", C.c_int), ("Cout", C.c_int), ("col0", C.c_int), ("block_cols", C.c_int), ("bias", C.c_void_p),
+                ("relu", C.c_int), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_scale", C.c_float),
+                ("out_ch_stride", C.c_int), ("res_hi", C.c_void_p), ("res_lo", C.c_void_p), ("res_scale", C.c_float),
+                ("out_f32", C.c_void_p)]
 
 
 class WireArgs(C.Structure):
@@ -142,6 +153,13 @@ def load_library():
     lib.pod_nms_fuse.argtypes = [C.POINTER(NmsArgs), C.c_void_p]
     lib.pod_cluster_merge.argtypes = [C.POINTER(MergeArgs), C.c_void_p]
     lib.pod_wire_records.argtypes = [C.POINTER(WireArgs), C.c_void_p]
+    lib.pod_conv_tc_general.argtypes = [C.POINTER(ConvGArgs), C.c_void_p]
+    lib.pod_pack_conv_weight_k.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pod_stem_conv7_pool.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                        C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                        C.c_void_p]
+    lib.pod_upsample2_add.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.pod_split_f32.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pod_q1_finish.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib

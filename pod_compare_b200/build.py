@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpodb200.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["api.cu", "prep.cu", "conv_simt.cu", "conv_tc.cu", "score.cu", "decode.cu", "nms.cu", "merge.cu", "wire.cu"]
+SOURCES = ["api.cu", "prep.cu", "conv_simt.cu", "conv_tc.cu", "score.cu", "decode.cu", "nms.cu", "merge.cu", "wire.cu", "backbone.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

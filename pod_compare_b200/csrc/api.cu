@@ -19,10 +19,11 @@ extern "C" __attribute__((visibility("default"))) int pod_version(void) { return
 // must never come back as a plausible-looking result.
 extern "C" __attribute__((visibility("default"))) int pod_status(int* status_host) {
   POD_REQUIRE(status_host, "pod_status: null");
-  int a = 0, b = 0, rc;
+  int a = 0, b = 0, c = 0, rc;
   if ((rc = pod_tc_status_fetch(&a))) return rc;
   if ((rc = pod_prep_status_fetch(&b))) return rc;
-  *status_host = a != 0 ? a : b;
+  if ((rc = pod_backbone_status_fetch(&c))) return rc;
+  *status_host = a != 0 ? a : (b != 0 ? b : c);
   return 0;
 }
 

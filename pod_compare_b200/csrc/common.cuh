@@ -15,6 +15,7 @@ void pod_set_error(const char* fmt, ...);
 // device-side error words of the kernel files (each reads and clears its own); combined by pod_status (api.cu)
 int pod_tc_status_fetch(int* v);
 int pod_prep_status_fetch(int* v);
+int pod_backbone_status_fetch(int* v);
 
 #define POD_REQUIRE(cond, ...)                                   \
   do {                                                           \

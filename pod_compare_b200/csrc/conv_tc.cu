@@ -73,6 +73,14 @@ struct Params {
   uint32_t drop_thr;
   float drop_scale;
   PhiloxKey key;
+  // generalised geometry (pod_conv_tc_general: backbone convolutions on the single-CTA kernel); the head's 3x3 / stride 1
+  // launches use taps = 9, ksz = 3, stride = 1, pad = 1, w_row0 = 0, out_ch_stride = Cout_pad, out_ch_off = 0
+  int taps, ksz, stride, pad;
+  int w_row0;                 // first row of this output-channel block in the packed weight matrix
+  int out_ch_stride, out_ch_off;
+  const __half* res_hi;       // optional residual (split pair, layout of the HIDDEN output) added before the ReLU
+  const __half* res_lo;
+  float res_inv_scale;
   // Q1 sample accumulation (CTA-pair kernel, last tower layer): see TileRef / tile_ref2 below
   int q1_mode;          // 0 = plain tile order
   int q1_samples;       // S: MC samples per image; maps of an image are ordered sample-major, pass-minor
@@ -424,9 +432,25 @@ __device__ __forceinline__ void tile_epilogue(const Params& P, const float (&sum
       const int ch = col0 + g * 16;
       float v[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        v[i] = fmaf(sum[g * 16 + i], acc_scale, __ldg(P.bias + ch + i));
-        if (P.relu) v[i] = fmaxf(v[i], 0.f);
+      for (int i = 0; i < 16; ++i) v[i] = fmaf(sum[g * 16 + i], acc_scale, __ldg(P.bias + ch + i));
+      if (MODE == POD_OUT_HIDDEN && P.res_hi != nullptr) {
+        // residual connection of a bottleneck block (detectron2 BottleneckBlock.forward: out += shortcut; relu)
+        const long long ro = ((long long)n * P.H * P.W + pixel) * P.out_ch_stride + P.out_ch_off + ch;
+        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(P.res_hi + ro)), h1 = __ldg(reinterpret_cast<const uint4*>(P.res_hi + ro) + 1);
+        const uint4 l0 = __ldg(reinterpret_cast<const uint4*>(P.res_lo + ro)), l1 = __ldg(reinterpret_cast<const uint4*>(P.res_lo + ro) + 1);
+        const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+          const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
+          v[2 * i] = __fadd_rn(v[2 * i], __fadd_rn(hf.x, lf.x) * P.res_inv_scale);
+          v[2 * i + 1] = __fadd_rn(v[2 * i + 1], __fadd_rn(hf.y, lf.y) * P.res_inv_scale);
+        }
+      }
+      if (P.relu) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
       }
       if (MODE == POD_OUT_HIDDEN) {
         if (P.drop_thr != 0u) {
@@ -447,7 +471,7 @@ __device__ __forceinline__ void tile_epilogue(const Params& P, const float (&sum
           ph[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
           pl[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
         }
-        const long long o = ((long long)n * P.H * P.W + pixel) * P.Cout_pad + ch;
+        const long long o = ((long long)n * P.H * P.W + pixel) * P.out_ch_stride + P.out_ch_off + ch;
         uint4* dh = reinterpret_cast<uint4*>(P.out_hi + o);
         uint4* dl = reinterpret_cast<uint4*>(P.out_lo + o);
         dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -537,7 +561,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
   const uint32_t tmem_base = tmem_base_s;
 
   const int kb_per_tap = P.Cin / BK;
-  const int kb_total = 9 * kb_per_tap;
+  const int kb_total = P.taps * kb_per_tap;
   const int kb_per_chunk = P.kb_per_chunk;
   const int n_chunks = kb_total / kb_per_chunk;
   const int tiles_per_map = P.tiles_x * P.tiles_y;
@@ -577,16 +601,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc(const __grid_cons
       for (int tile = blockIdx.x; tile < P.num_tiles && ok; tile += gridDim.x) {
         const int n = physical_map(P, tile / tiles_per_map), r = tile % tiles_per_map;
         const int y0 = (r / P.tiles_x) * TILE_H, x0 = (r % P.tiles_x) * TILE_W;
-        for (int tap = 0; tap < 9 && ok; ++tap) {
-          const int yy = y0 + tap / 3 - 1, xx = x0 + tap % 3 - 1;
+        for (int tap = 0; tap < P.taps && ok; ++tap) {
+          // input coordinates of the tile's first output pixel for this tap; a strided convolution reads every
+          // stride-th input pixel through the tensor map's element strides (the box is 16 x 8 loaded pixels either way)
+          const int yy = y0 * P.stride + tap / P.ksz - P.pad, xx = x0 * P.stride + tap % P.ksz - P.pad;
           for (int cb = 0; cb < kb_per_tap; ++cb) {
             if (!mbar_wait(&empty_bar[stage], phase ^ 1u, 1)) { ok = false; break; }
             mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)C::STAGE_BYTES);
             uint8_t* s = smem + (size_t)stage * C::STAGE_BYTES;
             tma_load_4d(&P.tm_a_hi, &full_bar[stage], s, cb * BK, xx, yy, n);
             tma_load_4d(&P.tm_a_lo, &full_bar[stage], s + C::A_BYTES, cb * BK, xx, yy, n);
-            tma_load_2d(&P.tm_b_hi, &full_bar[stage], s + 2 * C::A_BYTES, tap * P.Cin + cb * BK, 0);
-            tma_load_2d(&P.tm_b_lo, &full_bar[stage], s + 2 * C::A_BYTES + C::B_BYTES, tap * P.Cin + cb * BK, 0);
+            tma_load_2d(&P.tm_b_hi, &full_bar[stage], s + 2 * C::A_BYTES, tap * P.Cin + cb * BK, P.w_row0);
+            tma_load_2d(&P.tm_b_lo, &full_bar[stage], s + 2 * C::A_BYTES + C::B_BYTES, tap * P.Cin + cb * BK, P.w_row0);
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -1121,13 +1147,14 @@ static PFN_tmapEncodeTiled get_encode() {
 }
 
 static int encode_act(CUtensorMap* tm, const void* base, int Cin, int W, int H, int NB, long long map_stride_elems, int BK,
-                      int box_rows, int box_cols = TILE_W) {
+                      int box_rows, int box_cols = TILE_W, int stride = 1) {
   PFN_tmapEncodeTiled enc = get_encode();
   POD_REQUIRE(enc, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
   cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)map_stride_elems * 2};
-  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
-  cuuint32_t est[4] = {1, 1, 1, 1};
+  // a strided convolution loads every stride-th pixel: the box spans box * stride source pixels (traversal stride)
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(box_cols * stride), (cuuint32_t)(box_rows * stride), 1};
+  cuuint32_t est[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, est,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1621,6 +1648,8 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   if ((rc = encode_wt(&P.tm_b_hi, a->w_hi, 9 * a->Cin, a->Cout_pad, BK, b_box_rows))) return rc;
   if ((rc = encode_wt(&P.tm_b_lo, a->w_lo, 9 * a->Cin, a->Cout_pad, BK, b_box_rows))) return rc;
   P.NB = a->NB; P.H = a->H; P.W = a->W; P.Cin = a->Cin;
+  P.taps = 9; P.ksz = 3; P.stride = 1; P.pad = 1; P.w_row0 = 0;
+  P.out_ch_stride = a->Cout_pad; P.out_ch_off = 0;
   P.tiles_x = (a->W + TILE_W - 1) / TILE_W;
   P.tiles_y = (a->H + TILE_H - 1) / TILE_H;
   P.map_group = P.map_live = 1;
@@ -1688,7 +1717,7 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
                 "convolution on the CTA-pair kernel");
     POD_REQUIRE(a->q1_samples > 1 && (a->q1_passes == 1 || a->q1_passes == 2) && a->NB % (a->q1_samples * a->q1_passes) == 0,
                 "pod_conv3x3_tc: q1 maps must come as images x samples x passes");
-    POD_REQUIRE(a->q1_group > 0 && a->q1_acc_mask > 0 && a->q1_acc_mask < (1 << a->q1_passes), "pod_conv3x3_tc: bad q1 group / pass mask");
+    POD_REQUIRE(a->q1_group > 0 && a->q1_acc_mask >= 0 && a->q1_acc_mask < (1 << a->q1_passes), "pod_conv3x3_tc: bad q1 group / pass mask");
     POD_REQUIRE(a->q1_live[0] >= 0 && a->q1_live[0] <= a->q1_samples && a->q1_live[1] >= 0 && a->q1_live[1] <= a->q1_samples,
                 "pod_conv3x3_tc: q1_live out of range");
     POD_REQUIRE((uintptr_t)a->q1_acc % 16 == 0, "pod_conv3x3_tc: q1_acc must be 16-byte aligned");
@@ -1713,6 +1742,82 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
                                      : dispatch_bn<64, POD_OUT_RAW, false>(P, st);
   }
   return a->mode == POD_OUT_HIDDEN ? dispatch_bn<32, POD_OUT_HIDDEN, false>(P, st) : dispatch_bn<32, POD_OUT_RAW, false>(P, st);
+}
+
+// =====================================================================================================
+// General convolution entry (ResNet-50-FPN backbone): 1x1 or 3x3, stride 1 or 2, any Cin % 64 == 0,
+// output channels in column blocks of 64 / 128 / 256 out of one packed weight matrix, optional residual + ReLU.
+// Runs the single-CTA pixels-as-M kernel above (k_conv3x3_tc, per-tap operand staging) with the geometry in Params.
+// =====================================================================================================
+static int largest_chunk(int kb_total) {
+  for (int c = 12; c >= 1; --c)
+    if (kb_total % c == 0) return c;
+  return 1;
+}
+
+extern "C" __attribute__((visibility("default"))) int pod_conv_tc_general(const pod_convg_args* a, void* stream) {
+  using namespace tc;
+  POD_REQUIRE(a, "pod_conv_tc_general: null args");
+  POD_REQUIRE(a->in_hi && a->in_lo && a->w_hi && a->w_lo && a->bias, "pod_conv_tc_general: null operand");
+  POD_REQUIRE(a->ksize == 1 || a->ksize == 3, "pod_conv_tc_general: kernel size 1 or 3");
+  POD_REQUIRE(a->stride == 1 || a->stride == 2, "pod_conv_tc_general: stride 1 or 2");
+  POD_REQUIRE(a->NB > 0 && a->Hin > 0 && a->Win > 0 && a->Cin >= 64 && a->Cin % 64 == 0, "pod_conv_tc_general: bad input shape (Cin%%64)");
+  POD_REQUIRE(a->Cout > 0 && a->block_cols > 0 && a->col0 >= 0 && a->col0 + a->block_cols <= a->Cout_rows,
+              "pod_conv_tc_general: column block outside the packed weight matrix");
+  POD_REQUIRE(a->block_cols == 64 || a->block_cols == 128 || a->block_cols == 256, "pod_conv_tc_general: block of 64, 128 or 256 columns");
+  POD_REQUIRE(((uintptr_t)a->in_hi | (uintptr_t)a->in_lo | (uintptr_t)a->w_hi | (uintptr_t)a->w_lo) % 16 == 0,
+              "pod_conv_tc_general: operands must be 16-byte aligned");
+  POD_REQUIRE(a->in_scale > 0.f && a->w_scale > 0.f, "pod_conv_tc_general: scales must be positive");
+  const int pad = a->ksize / 2;
+  const int Hout = (a->Hin + 2 * pad - a->ksize) / a->stride + 1, Wout = (a->Win + 2 * pad - a->ksize) / a->stride + 1;
+  POD_REQUIRE(Hout == a->Hout && Wout == a->Wout, "pod_conv_tc_general: output size %dx%d expected, got %dx%d", Hout, Wout, a->Hout, a->Wout);
+  Params P;
+  memset(&P, 0, sizeof(P));
+  int rc;
+  if ((rc = encode_act(&P.tm_a_hi, a->in_hi, a->Cin, a->Win, a->Hin, a->NB, (long long)a->Hin * a->Win * a->Cin, 64, TILE_H, TILE_W, a->stride))) return rc;
+  if ((rc = encode_act(&P.tm_a_lo, a->in_lo, a->Cin, a->Win, a->Hin, a->NB, (long long)a->Hin * a->Win * a->Cin, 64, TILE_H, TILE_W, a->stride))) return rc;
+  const int taps = a->ksize * a->ksize;
+  if ((rc = encode_wt(&P.tm_b_hi, a->w_hi, taps * a->Cin, a->Cout_rows, 64, a->block_cols))) return rc;
+  if ((rc = encode_wt(&P.tm_b_lo, a->w_lo, taps * a->Cin, a->Cout_rows, 64, a->block_cols))) return rc;
+  P.NB = a->NB; P.H = Hout; P.W = Wout; P.Cin = a->Cin;
+  P.taps = taps; P.ksz = a->ksize; P.stride = a->stride; P.pad = pad; P.w_row0 = a->col0;
+  P.tiles_x = (Wout + TILE_W - 1) / TILE_W;
+  P.tiles_y = (Hout + TILE_H - 1) / TILE_H;
+  P.map_group = P.map_live = 1;
+  const long long nt = (long long)P.tiles_x * P.tiles_y * a->NB;
+  POD_REQUIRE(nt < (1ll << 31), "pod_conv_tc_general: too many tiles");
+  P.num_tiles = (int)nt;
+  const int live = a->Cout - a->col0 < a->block_cols ? a->Cout - a->col0 : a->block_cols;   // real channels of this block
+  P.Cout = live; P.Cout_pad = a->block_cols;
+  P.relu = a->relu;
+  P.kb_per_chunk = largest_chunk(taps * (a->Cin / 64));
+  P.acc_scale = 1.0f / (a->in_scale * a->w_scale) * trunc_comp_factor(P.kb_per_chunk, 64, a->block_cols <= 128 ? 2 : 3);
+  P.bias = a->bias + a->col0;
+  P.out_ch_stride = a->out_ch_stride; P.out_ch_off = a->col0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->out_f32 != nullptr) {
+    // fp32 channels-last output (FPN maps handed to the head): element (n, pixel, c) at n*Hout*Wout*stride + pixel*stride + c
+    P.out_f32 = a->out_f32 + a->col0;
+    P.out_map_stride = (long long)Hout * Wout * a->out_ch_stride; P.out_pixel_stride = a->out_ch_stride;
+    switch (a->block_cols) {
+      case 256: return launch<256, 64, POD_OUT_RAW, false>(P, st);
+      case 128: return launch<128, 64, POD_OUT_RAW, false>(P, st);
+      default: return launch<64, 64, POD_OUT_RAW, false>(P, st);
+    }
+  }
+  POD_REQUIRE(a->out_hi && a->out_lo && a->out_scale > 0.f && live == a->block_cols, "pod_conv_tc_general: split output needs out_hi / out_lo / "
+              "out_scale and a full column block");
+  POD_REQUIRE(((uintptr_t)a->out_hi | (uintptr_t)a->out_lo) % 16 == 0 && a->out_ch_stride % 8 == 0, "pod_conv_tc_general: outputs must be 16-byte aligned");
+  P.out_hi = (__half*)a->out_hi; P.out_lo = (__half*)a->out_lo; P.out_scale = a->out_scale;
+  if (a->res_hi != nullptr) {
+    POD_REQUIRE(a->res_lo && a->res_scale > 0.f && ((uintptr_t)a->res_hi | (uintptr_t)a->res_lo) % 16 == 0, "pod_conv_tc_general: bad residual");
+    P.res_hi = (const __half*)a->res_hi; P.res_lo = (const __half*)a->res_lo; P.res_inv_scale = 1.0f / a->res_scale;
+  }
+  switch (a->block_cols) {
+    case 256: return launch<256, 64, POD_OUT_HIDDEN, false>(P, st);
+    case 128: return launch<128, 64, POD_OUT_HIDDEN, false>(P, st);
+    default: return launch<64, 64, POD_OUT_HIDDEN, false>(P, st);
+  }
 }
 
 int pod_tc_status_fetch(int* v) {

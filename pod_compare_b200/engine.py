@@ -136,6 +136,7 @@ class HeadEngine:
         self.ws = weight_sets
         self.device = torch.device(device)
         self._buf = {}
+        self.profile_layers = False       # bench --profile-layers: tag tower launches by layer in ops.PROFILE
 
     # ------------------------------------------------------------------ buffers (reused across calls)
     def _get(self, name, numel, dtype):
@@ -154,13 +155,29 @@ class HeadEngine:
         (hi, lo) pair is scaled, so results do not depend on the scale beyond fp16 round-off; a power-of-two scale
         makes the rescaling exact.  Computed by two small kernels into a device word that every kernel of the call
         reads: no torch ops, no host sync (non-finite inputs raise through ops.check_status at the end of the call)."""
-        return ops.feature_scale_dev(feats, ACT_SCALE, FEATURE_TARGET)
+        return ops.feature_scale_dev([HeadEngine._flat(f) for f in feats], ACT_SCALE, FEATURE_TARGET)
 
-    def _conv_hidden(self, src, NB, H, W, pcv, dst, drop, scale_dev, map_group=0, map_live=0):
+    @staticmethod
+    def _is_channels_last(f):
+        """(B, C, H, W)-shaped view of channels-last memory (what backbone_tc returns): no layout pass needed."""
+        return f.dim() == 4 and not f.is_contiguous() and f.permute(0, 2, 3, 1).is_contiguous()
+
+    @classmethod
+    def _flat(cls, f):
+        return f.permute(0, 2, 3, 1) if cls._is_channels_last(f) else f.contiguous()
+
+    @classmethod
+    def _split_input(cls, f, scale_dev):
+        """FPN map -> channels-last fp16 split pair scaled by the call's device-resident scale."""
+        if cls._is_channels_last(f):
+            return ops.split_f32(f.permute(0, 2, 3, 1), scale_dev=scale_dev)
+        return ops.nchw_to_nhwc_split_dev(f.contiguous(), scale_dev)
+
+    def _conv_hidden(self, src, NB, H, W, pcv, dst, drop, scale_dev, map_group=0, map_live=0, tag=None):
         """256 -> 256 tower layer; `scale_dev` is the call's activation scale (input and output pairs)."""
         ops.conv3x3_tc(src[0], src[1], 1.0, NB, H, W, 256, pcv.w_hi, pcv.w_lo, pcv.w_scale, pcv.bias, pcv.cout,
                        pcv.cout_pad, POD_OUT_HIDDEN, True, out_hi=dst[0], out_lo=dst[1], out_scale=1.0, drop=drop,
-                       map_group=map_group, map_live=map_live, in_scale_dev=scale_dev, out_scale_dev=scale_dev)
+                       map_group=map_group, map_live=map_live, in_scale_dev=scale_dev, out_scale_dev=scale_dev, tag=tag)
 
     def _conv_out(self, src, NB, H, W, blocks, out, out_offset, out_map_stride, scale_dev, in_map_stride=None, in_offset=0,
                   map_group=0, map_live=0):
@@ -223,7 +240,7 @@ class HeadEngine:
         for lvl, f in enumerate(feats):
             H, W = level_hw[lvl]
             HW = H * W
-            fhi, flo = ops.nchw_to_nhwc_split_dev(f.contiguous(), fscale)
+            fhi, flo = self._split_input(f, fscale)
             for tower in (TOWER_CLS, TOWER_BOX):
                 tw = w.towers[tower]
                 has_var = pc.cls_var if tower == TOWER_CLS else pc.bbox_cov
@@ -260,7 +277,8 @@ class HeadEngine:
                                            "mask": acc_mask, "group": Q1_GROUP})
                         ops.q1_finish(q1_acc, B * n_acc, groups, HW * 256, n_mc, fscale, q1_mean[0], q1_mean[1])
                     else:
-                        self._conv_hidden(act[cur], NB, H, W, tw[layer], act[cur ^ 1], d, fscale, map_group=grp, map_live=live)
+                        self._conv_hidden(act[cur], NB, H, W, tw[layer], act[cur ^ 1], d, fscale, map_group=grp, map_live=live,
+                                          tag="tower256" if not self.profile_layers else "tower256_L%d" % layer)
                     cur ^= 1
                 n_live = n_mc - 1 if (skip_unread and n_mc > 1) else n_mc        # samples whose mean/var heads are read
                 # output convs: pass-0 maps feed the mean head, pass-1 maps the variance head (Q2)
@@ -331,7 +349,7 @@ class HeadEngine:
         fscales = [self.feature_scale(fs) for fs in feat_sets]
         for lvl in range(len(feats)):
             H, W = level_hw[lvl]
-            split_maps = [ops.nchw_to_nhwc_split_dev(fs[lvl].contiguous(), sc) for fs, sc in zip(feat_sets, fscales)]
+            split_maps = [self._split_input(fs[lvl], sc) for fs, sc in zip(feat_sets, fscales)]
             for e, mi in enumerate(members):
                 w = self.ws[mi]
                 (fhi, flo), fscale = split_maps[e if per_member_feats else 0], fscales[e if per_member_feats else 0]

@@ -10,7 +10,7 @@ import math
 import torch
 
 from . import _cabi
-from ._cabi import (POD_OUT_HIDDEN, POD_OUT_RAW, ConvArgs, DecodeArgs, Dropout, MergeArgs, NmsArgs, WireArgs, check, int_array,
+from ._cabi import (POD_OUT_HIDDEN, POD_OUT_RAW, ConvArgs, ConvGArgs, DecodeArgs, Dropout, MergeArgs, NmsArgs, WireArgs, check, int_array,
                     ptr, stream_ptr)
 
 _launches = 0
@@ -174,7 +174,7 @@ def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias,
                out_hi=None, out_lo=None, out_scale=1.0, out_f32=None, out_map_stride=0, out_pixel_stride=0,
                drop=None, in_map_stride=None, in_offset=0, out_offset=0, out2_f32=None, out2_offset=0, split_col=0,
                out2_map_stride=0, out2_pixel_stride=0, map_group=0, map_live=0, in_scale_dev=None, out_scale_dev=None,
-               q1=None):
+               q1=None, tag=None):
     """Raw-pointer launch of the tcgen05 convolution. `in_offset`/`out_offset` are ELEMENT offsets
     into in_hi/in_lo and out_f32.  in_scale_dev: 1-element fp32 CUDA tensor replacing in_scale."""
     lib = _cabi.require_device()
@@ -212,7 +212,9 @@ def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias,
     check(lib.pod_conv3x3_tc(C.byref(a), stream_ptr()), "pod_conv3x3_tc")
     if PROFILE is not None:
         e1.record()
+        user_tag = tag
         tag = "tower256" if (Cout_pad == 256 and mode == POD_OUT_HIDDEN) else ("conv1" if Cout_pad == 256 else "out")
+        tag = user_tag or tag
         if q1 is not None:
             tag = "tower256_q1"
         maps = NB if not map_group else NB // map_group * map_live          # maps actually evaluated
@@ -232,7 +234,8 @@ def conv3x3_tc_status():
 STATUS_TEXT = {100: "a hidden tower activation left the fp16 split range (|x| * 16 > 65504): the checkpoint / input "
                     "produces activations this path cannot represent",
                101: "a first-layer tower activation left the fp16 split range (|x| * 16 / (1-p) > 65504)",
-               102: "non-finite values in the input feature maps"}
+               102: "non-finite values in the input feature maps",
+               103: "a backbone feature map left the fp16 split range"}
 
 
 def status():
@@ -512,3 +515,84 @@ def q1_finish(acc, n_maps, groups, n, samples, scale_dev, out_hi, out_lo):
     check(lib.pod_q1_finish(ptr(acc), int(n_maps), int(groups), int(n), int(samples), 1.0, ptr(scale_dev), ptr(out_hi), ptr(out_lo),
                             stream_ptr()), "pod_q1_finish")
     _count()
+
+
+# --------------------------------------------------------------------------------------------------- backbone ops
+def pack_conv_weight_k(w, cout_pad, scale):
+    """(Cout, Cin, k, k) fp32 -> [cout_pad][k*k*Cin] split pair (hi rows then lo rows in one buffer)."""
+    lib = _cabi.require_device()
+    _chk(w, torch.float32, "w")
+    cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+    both = torch.empty((2 * cout_pad, k * k * cin), dtype=torch.float16, device=w.device)
+    hi, lo = both[:cout_pad], both[cout_pad:]
+    check(lib.pod_pack_conv_weight_k(ptr(w), cout, cin, k, cout_pad, scale, ptr(hi), ptr(lo), stream_ptr()), "pod_pack_conv_weight_k")
+    _count()
+    return hi, lo
+
+
+def conv_tc_general(x_hi, x_lo, in_scale, NB, Hin, Win, Cin, ksize, stride, w_hi, w_lo, w_scale, cout_rows, cout, bias, relu,
+                    block_cols, out_hi=None, out_lo=None, out_scale=1.0, out_ch_stride=None, res=None, res_scale=1.0, out_f32=None):
+    """One convolution of the backbone = one tcgen05 launch per column block of `block_cols` output channels."""
+    lib = _cabi.require_device()
+    pad = ksize // 2
+    Hout, Wout = (Hin + 2 * pad - ksize) // stride + 1, (Win + 2 * pad - ksize) // stride + 1
+    a = ConvGArgs()
+    a.in_hi, a.in_lo, a.in_scale = x_hi.data_ptr(), x_lo.data_ptr(), float(in_scale)
+    a.NB, a.Hin, a.Win, a.Cin, a.ksize, a.stride, a.Hout, a.Wout = NB, Hin, Win, Cin, ksize, stride, Hout, Wout
+    a.w_hi, a.w_lo, a.w_scale = w_hi.data_ptr(), w_lo.data_ptr(), float(w_scale)
+    a.Cout_rows, a.Cout, a.block_cols = cout_rows, cout, block_cols
+    a.bias, a.relu = bias.data_ptr(), int(bool(relu))
+    a.out_hi = out_hi.data_ptr() if out_hi is not None else None
+    a.out_lo = out_lo.data_ptr() if out_lo is not None else None
+    a.out_scale = float(out_scale)
+    a.out_ch_stride = int(out_ch_stride if out_ch_stride is not None else cout_rows)
+    if res is not None:
+        a.res_hi, a.res_lo, a.res_scale = res[0].data_ptr(), res[1].data_ptr(), float(res_scale)
+    a.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    for col0 in range(0, cout_rows, block_cols):
+        if col0 >= cout:
+            break
+        a.col0 = col0
+        check(lib.pod_conv_tc_general(C.byref(a), stream_ptr()), "pod_conv_tc_general")
+        _count()
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append((e0, e1, 2.0 * ksize * ksize * Cin * cout * NB * Hout * Wout, "backbone_conv"))
+    return Hout, Wout
+
+
+def stem_conv7_pool(images, H, W, mean, std, w147x64, bias, scratch, out_hi, out_lo, out_scale):
+    lib = _cabi.require_device()
+    NB, _, Himg, Wimg = images.shape
+    assert images.is_cuda and images.is_contiguous() and images.dtype in (torch.uint8, torch.float32)
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    sd = (C.c_float * 3)(*[float(v) for v in std])
+    check(lib.pod_stem_conv7_pool(ptr(images), int(images.dtype == torch.uint8), NB, Himg, Wimg, H, W, m, sd, ptr(w147x64), ptr(bias),
+                                  ptr(scratch), ptr(out_hi), ptr(out_lo), float(out_scale), stream_ptr()), "pod_stem_conv7_pool")
+    _count(2)
+
+
+def upsample2_add(dst, src):
+    """dst (NB,H,W,C) fp32 += nearest x2 upsample of src (NB,ceil(H/2),ceil(W/2),C)."""
+    lib = _cabi.require_device()
+    NB, H, W, Cn = dst.shape
+    assert tuple(src.shape) == (NB, (H + 1) // 2, (W + 1) // 2, Cn)
+    check(lib.pod_upsample2_add(ptr(_chk(dst, torch.float32, "dst")), ptr(_chk(src, torch.float32, "src")), NB, H, W, Cn, stream_ptr()),
+          "pod_upsample2_add")
+    _count()
+
+
+def split_f32(x, scale=1.0, scale_dev=None, relu=False, out_hi=None, out_lo=None):
+    """fp32 tensor (any shape, numel % 8 == 0) -> fp16 split pair of x * scale (or * *scale_dev)."""
+    lib = _cabi.require_device()
+    _chk(x, torch.float32, "x")
+    if out_hi is None:
+        out_hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+        out_lo = torch.empty_like(out_hi)
+    check(lib.pod_split_f32(ptr(x), x.numel(), float(scale), ptr(scale_dev), int(bool(relu)), ptr(out_hi), ptr(out_lo), stream_ptr()),
+          "pod_split_f32")
+    _count()
+    return out_hi, out_lo

@@ -137,16 +137,20 @@ class ProbabilisticPredictor:
         self._engine = HeadEngine(self.path_config(), self.weight_sets, self.device)
         return self
 
-    def load_backbone(self, state_dicts):
+    def load_backbone(self, state_dicts, impl="tc"):
         """Install the ResNet-50-FPN feature extractor (detectron2 key names, backbone.py) so that
         `predictor(input_im)` accepts raw images.  One state dict, or E of them for INFERENCE_MODE 'ensembles':
         every ensemble member of the reference is a full model with its own backbone, hence its own feature maps
         (reference probabilistic_inference.py:58-77,499-501; probabilistic_retinanet.py:99)."""
-        from .backbone import ResNetFPNBackbone
         if isinstance(state_dicts, dict):
             state_dicts = [state_dicts]
-        nets = [ResNetFPNBackbone(sd, self.cfg.MODEL.PIXEL_MEAN, self.cfg.MODEL.PIXEL_STD, self.device)
-                for sd in state_dicts]
+        if impl == "tc":
+            from .backbone_tc import TcResNetFPNBackbone as Net      # hand-written sm_100a kernels (default)
+        elif impl == "torch":
+            from .backbone import ResNetFPNBackbone as Net           # torch library convolutions: the oracle of backbone_tc
+        else:
+            raise ValueError("backbone impl must be 'tc' or 'torch'")
+        nets = [Net(sd, self.cfg.MODEL.PIXEL_MEAN, self.cfg.MODEL.PIXEL_STD, self.device) for sd in state_dicts]
         self.backbone = nets[0]
         self.member_backbones = nets if len(nets) > 1 else None
         return self
@@ -255,7 +259,9 @@ class ProbabilisticPredictor:
         seed = self.rng_seed if seed is None else seed
         eng = self._engine
         def to_dev(fs):
-            return [f.to(self.device, dtype=torch.float32, non_blocking=True).contiguous() for f in fs]
+            # channels-last views (backbone_tc output) keep their layout; everything else becomes NCHW-contiguous
+            return [f if (f.is_cuda and f.dtype == torch.float32 and HeadEngine._is_channels_last(f))
+                    else f.to(self.device, dtype=torch.float32, non_blocking=True).contiguous() for f in fs]
         feats = [to_dev(fs) for fs in feats] if per_member else to_dev(feats)
         level_hw = [tuple(f.shape[-2:]) for f in (feats[0] if per_member else feats)]
         anchors = self._anchors(level_hw)

@@ -39,6 +39,18 @@ def _cov_close(got, ref, tol):
     return bool((np.abs(got - ref) <= tol * scale + 1e-7).all())
 
 
+def _close(got, ref, rtol, atol, what):
+    """np.allclose with a diagnosis: where and by how much the worst element deviates."""
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    excess = np.abs(got - ref) - (atol + rtol * np.abs(ref))
+    if excess.size and excess.max() > 0:
+        i = np.unravel_index(int(excess.argmax()), excess.shape)
+        raise AssertionError("%s: worst element %s got %.9g ref %.9g (abs %.3g, rel %.3g; rtol %g atol %g); %d of %d outside"
+                             % (what, i, got[i], ref[i], abs(got[i] - ref[i]), abs(got[i] - ref[i]) / max(abs(ref[i]), 1e-300),
+                                rtol, atol, int((excess > 0).sum()), excess.size))
+    return True
+
+
 def _oracle_case(name, keep_diag=False):
     opts, mode, n_mc, seeds, hw, out_hw, seed, img = C.CASES[name]
     cfg = C.build_cfg(name)
@@ -293,7 +305,7 @@ def _align_by_id(ids_got, ids_ref, scores_ref, boundary_scores, group_of=None):
     return ig, ir
 
 
-def _compare_path(res, cand, det, ref_final, ref_cand, ref_det, pp, bayes, prob_atol=1e-7):
+def _compare_path(res, cand, det, ref_final, ref_cand, ref_det, pp, bayes, prob_atol=1e-7, prob_rtol=1e-4):
     M = int(cand["count"][0])
     ids_got = cand["anchor"][0, :M].cpu().numpy()
     sizes = np.cumsum([0] + [int(x.shape[0]) for x in ref_cand.level_scores])
@@ -311,9 +323,9 @@ def _compare_path(res, cand, det, ref_final, ref_cand, ref_det, pp, bayes, prob_
     assert len(ig) >= 0.98 * len(ref_cand.anchor_ids)
     g = lambda k: cand[k][0, :M].cpu().numpy()[ig]
     assert np.array_equal(g("classes").astype(np.int64), ref_cand.classes.numpy()[ir])
-    assert np.allclose(g("scores"), ref_cand.scores.numpy()[ir], rtol=1e-4, atol=prob_atol)
-    assert np.allclose(g("probs"), ref_cand.probs.numpy()[ir], rtol=1e-4, atol=prob_atol)
-    assert np.allclose(g("boxes"), ref_cand.boxes.numpy()[ir], rtol=1e-4, atol=2e-3)
+    assert _close(g("scores"), ref_cand.scores.numpy()[ir], prob_rtol, prob_atol, "candidate scores")
+    assert _close(g("probs"), ref_cand.probs.numpy()[ir], prob_rtol, prob_atol, "candidate probability vectors")
+    assert _close(g("boxes"), ref_cand.boxes.numpy()[ir], 1e-4, 2e-3, "candidate boxes")
     if isinstance(ref_cand.cov, torch.Tensor):
         assert _cov_close(g("cov"), ref_cand.cov.numpy()[ir], 2e-4)
     # detections: identified by the anchor id of the NMS survivor they come from
@@ -332,10 +344,9 @@ def _compare_path(res, cand, det, ref_final, ref_cand, ref_det, pp, bayes, prob_
     i_g = np.array([x[0] for x in sel], dtype=np.int64)
     i_r = np.array([x[1] for x in sel], dtype=np.int64)
     assert np.array_equal(res.pred_classes.cpu().numpy()[i_g], ref_final.classes.numpy()[i_r])
-    assert np.allclose(res.scores.cpu().numpy()[i_g], ref_final.scores.numpy()[i_r], rtol=1e-4, atol=prob_atol)
-    assert np.allclose(res.pred_cls_probs.cpu().numpy()[i_g], ref_final.probs.numpy()[i_r], rtol=1e-4, atol=prob_atol)
-    assert np.allclose(res.pred_boxes.tensor.cpu().numpy()[i_g], ref_final.boxes.numpy()[i_r], rtol=1e-4,
-                       atol=2e-2 if bayes else 2e-3)
+    assert _close(res.scores.cpu().numpy()[i_g], ref_final.scores.numpy()[i_r], prob_rtol, prob_atol, "scores")
+    assert _close(res.pred_cls_probs.cpu().numpy()[i_g], ref_final.probs.numpy()[i_r], prob_rtol, prob_atol, "probability vectors")
+    assert _close(res.pred_boxes.tensor.cpu().numpy()[i_g], ref_final.boxes.numpy()[i_r], 1e-4, 2e-2 if bayes else 2e-3, "boxes")
     assert _cov_close(res.pred_boxes_covariance.cpu().numpy()[i_g], ref_final.cov.numpy()[i_r], 2e-3 if bayes else 2e-4)
     # output order: descending score up to near-ties
     sc = res.scores.cpu().numpy()
@@ -584,9 +595,11 @@ def test_predictor_from_raw_images_with_backbone():
     cpu_feats = [f.cpu() for f in feats]
     ref_final, ref_cand, ref_det = O.predict(cpu_feats, [O.unpack_head(sds[0], pp)], pp, mode, (96, 160), seed=pred.rng_seed,
                                              image=0, return_candidates=True, keep_diag=True)
-    # logits of magnitude ~20: a probability e^-17 moves by 1e-4 relative per 1e-4 ABSOLUTE logit error (6 ulp of the
-    # logit itself), so the tiny class probabilities are compared with an absolute floor
-    _compare_path(ref[0], cand, det, ref_final, ref_cand, ref_det, pp, False, prob_atol=2e-6)
+    # These maps are ~15x larger than unit-variance features, and so are the logits (|logit| up to ~40).  A probability
+    # moves by dp/p = (1 - p) * d(logit): the head's ~1e-5 relative accuracy of the largest logit is an
+    # ABSOLUTE logit error of up to ~4e-4 here, i.e. up to 4e-4 relative on a probability -- the same conditioning limits
+    # any fp32 evaluation, the reference's included.  Measured worst case 2.0e-4 (r2f); bound 5e-4, floor 2e-6.
+    _compare_path(ref[0], cand, det, ref_final, ref_cand, ref_det, pp, False, prob_atol=2e-6, prob_rtol=5e-4)
 
 
 def test_large_feature_magnitudes_are_rescaled():
