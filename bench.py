@@ -89,16 +89,20 @@ def head_state_dicts(members, use_dropout, cls_var, bbox_cov):
 
 def workload_config(args, world):
     desc, _, mc, members = WORKLOADS[args.workload]
-    return {"workload": "%s, %s, batch %d per GPU, 1280x720 (FPN features in, detections out)"
-                        % (desc, ("N=%d" % args.n_mc) if mc else ("E=%d" % members if members > 1 else "N=1"), args.batch),
+    io = ("raw uint8 frames in (ResNet-50-FPN backbone inside the step: %s; frames padded to 736x1280), detections out"
+          % ("this repository's kernels" if getattr(args, "backbone", "tc") == "tc" else "torch library fp32 convolutions")
+          ) if getattr(args, "from_images", False) else "FPN features in, detections out"
+    return {"workload": "%s, %s, batch %d per GPU, 1280x720 (%s)"
+                        % (desc, ("N=%d" % args.n_mc) if mc else ("E=%d" % members if members > 1 else "N=1"), args.batch, io),
             "global_batch": args.batch * world, "batch_per_gpu": args.batch, "mc_samples": args.n_mc,
-            "image": "%dx%d" % (WIDTH, HEIGHT), "chunk_images": args.chunk,
+            "image": "%dx%d" % (WIDTH, HEIGHT), "chunk_images": args.chunk, "cuda_graph": bool(getattr(args, "cuda_graph", False)),
             "parallelism": "image-sharded dp%d + NCCL all-gather of detections" % world,
             "l2": "working set per step (tens of GB of activations) far exceeds the 126 MB L2; no flush needed",
             "sample_mean": ("per-sample output convolutions, outputs averaged (as the reference evaluates it)"
                             if (getattr(args, "no_fuse_q1", False) or getattr(args, "keep_unread", False) or not mc) else
-                            "last tower layer accumulated over the samples in the conv epilogue; cls_score / cls_var / bbox_cov "
-                            "run once per image (mean of a linear head = head of the mean; fp32 round-off apart, same result)"),
+                            "sample mean taken of the last tower layer (%s); cls_score / cls_var / bbox_cov run once per image "
+                            "(mean of a linear head = head of the mean; fp32 round-off apart, same result)"
+                            % ("tcgen05 epilogue accumulation" if getattr(args, "q1_epilogue", False) else "one streaming pass")),
             "unread_outputs": ("evaluated" if getattr(args, "keep_unread", False) else
                                "left out: box_cls / box_cls_var / box_reg_var of the last sample are never read by the "
                                "reference (probabilistic_inference.py:216-267); detections are bit-identical either way")}
@@ -261,9 +265,20 @@ def main():
     ap.add_argument("--keep-unread", action="store_true",
                     help="also evaluate the last sample's class / variance tower passes, whose outputs the reference "
                          "computes but never reads (default: left out, results identical)")
+    ap.add_argument("--q1-epilogue", action="store_true",
+                    help="form the sample mean of the last tower layer inside the tcgen05 epilogue instead of by the streaming pass")
     ap.add_argument("--no-fuse-q1", action="store_true",
                     help="evaluate cls_score / cls_var / bbox_cov for every MC sample and average the outputs (as the reference "
                          "does) instead of accumulating the last tower layer over the samples (default: fused)")
+    ap.add_argument("--from-images", action="store_true",
+                    help="side measurement: a step starts from raw uint8 frames and includes the ResNet-50-FPN backbone on this "
+                         "repository's kernels (frames padded to 736x1280 as detectron2 does); default: FPN features in")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="single-forward workloads: capture the whole step (backbone + head + post-processing) in a CUDA graph and "
+                         "replay it (launch-bound small batches); the batch must fit one chunk")
+    ap.add_argument("--backbone", default="tc", choices=["tc", "torch"],
+                    help="with --from-images: tc = this repository's kernels (default), torch = library fp32 convolutions (the "
+                         "oracle of backbone_tc.py, for comparison)")
     ap.add_argument("--profile-layers", action="store_true", help="report tower time per layer in ms_per_step_by_kernel")
     ap.add_argument("--halo", type=int, default=-1, help="row-halo activation staging: bit 0 = pixels-as-M kernels, bit 1 = weights-as-A kernel (default 3)")
     ap.add_argument("--chunk-taps", type=int, default=0, help="taps per accumulation chunk (1, 3, 9)")
@@ -301,17 +316,25 @@ def main():
     pred = build_predictor(cfg)
     m = pred.model
     members = WORKLOADS[args.workload][3]
+    mc_workload = WORKLOADS[args.workload][2]
     sds = head_state_dicts(members, m.use_dropout, m.compute_cls_var, m.compute_bbox_cov)
     pred.load_weight_sets(sds if members > 1 else sds[0])
     pred.skip_unread_outputs = not args.keep_unread
-    pred.fuse_sample_mean = not args.no_fuse_q1
+    pred.fuse_sample_mean = False if args.no_fuse_q1 else ("epilogue" if args.q1_epilogue else "stream")
     pred._engine.profile_layers = args.profile_layers
     B = args.batch
     # synthetic FPN features of this rank's images (weak scaling: B images per GPU)
     img0 = rank * B
     host_feats = None
     # every image of the batch is distinct (seeded by its global image id)
-    if members > 1:
+    if args.from_images:
+        from pod_compare_b200 import backbone as BB
+        bsd = [BB.random_state_dict(e) for e in range(members)]
+        pred.load_backbone(bsd if members > 1 else bsd[0], impl=args.backbone)
+        host_feats = torch.stack([S.make_image(0, img0 + i, HEIGHT, WIDTH) for i in range(B)]).pin_memory()
+        dev_feats = host_feats.cuda(non_blocking=True)
+        h2d_bytes = host_feats.numel()
+    elif members > 1:
         # ensembles: every member is a full model with its own backbone, hence its own feature maps (feats[e][l])
         per = [S.make_member_features(members, img0 + i, HEIGHT, WIDTH) for i in range(B)]
         host_feats = [[torch.cat([per[i][e][l] for i in range(B)], 0).pin_memory() for l in range(5)] for e in range(members)]
@@ -322,14 +345,25 @@ def main():
         host_feats = [torch.cat([per[i][l] for i in range(B)], 0).pin_memory() for l in range(5)]
         dev_feats = [f.cuda(non_blocking=True) for f in host_feats]
         h2d_bytes = sum(f.numel() * 4 for f in host_feats)
-    del per
     torch.cuda.synchronize()
 
+    runner = None
+    if args.cuda_graph:
+        if mc_workload or args.chunk < B:
+            raise SystemExit("--cuda-graph is for the single-forward workloads with --chunk >= --batch")
+        runner = pred.capture(dev_feats, out_hw=(HEIGHT, WIDTH), image0=img0)
+
     def step(feats):
+        if runner is not None:
+            _, det = runner(feats)           # copies the (host or device) inputs into the captured buffers, replays
+            return D.all_gather_records(D.pack_records(det))
         # one public-API call per step: the predictor evaluates the batch in chunks of args.chunk images and, for
         # host-resident features, uploads chunk i+1 on a copy stream while chunk i computes
-        _, _, cand, det = pred.infer_from_features(feats, (HEIGHT, WIDTH), (HEIGHT, WIDTH), image0=img0,
-                                                   return_candidates=True, chunk_images=args.chunk)
+        if args.from_images:
+            _, det = pred.infer_from_images(feats, (HEIGHT, WIDTH), image0=img0, chunk_images=args.chunk, return_det=True)
+        else:
+            _, _, cand, det = pred.infer_from_features(feats, (HEIGHT, WIDTH), (HEIGHT, WIDTH), image0=img0,
+                                                       return_candidates=True, chunk_images=args.chunk)
         return D.all_gather_records(D.pack_records(det))
 
     def barrier():
@@ -407,7 +441,7 @@ def main():
         for (s, e, flop, tag) in prof:
             d = s.elapsed_time(e)
             by_tag[tag] = by_tag.get(tag, 0.0) + d / args.steps
-            if tag in ("mask_expand", "sample_mean"):
+            if tag in ("mask_expand", "sample_mean", "act_mean"):
                 h = hbm.setdefault(tag, [0.0, 0.0, 0])
                 h[0] += d; h[1] += flop; h[2] += 1
                 continue
@@ -442,7 +476,8 @@ def main():
     hbm_kernels = {}
     if prof:
         names = {"mask_expand": "k_mask_expand (first-layer MC replication: 1 fp32 read, N x passes split-pair writes)",
-                 "sample_mean": "k_sample_mean_q1 (per-anchor statistics: Q1 mean over the N samples)"}
+                 "sample_mean": "k_sample_mean_q1 (per-anchor statistics: Q1 mean over the N samples)",
+                 "act_mean": "k_q1_mean_act (Q1 mean of the last tower layer over the N samples: the cov-head statistics stream)"}
         for tag, (t_ms, nbytes, cnt) in hbm.items():
             gbs = nbytes / (t_ms / 1000.0) / 1e9
             hbm_kernels[tag] = {"kernel": names[tag], "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",

@@ -204,6 +204,9 @@ int pod_conv3x3_tc_status(int* status_host);
  * CTA expire and the error path (pod_status != 0 -> PodError in the predictor) can be exercised. */
 int pod_conv3x3_tc_set_wait_limit(long long cycles);
 int pod_conv3x3_tc_debug_fault(int on);
+/* Measurement hook: enable (out == NULL), then after CTA-pair launches read {SM cycles, nanoseconds} of the last one
+ * (out = 2 words, synchronises): cycles / ns is the clock the tensor kernel really ran at under the power cap. */
+int pod_conv3x3_tc_debug_clock(int enable, long long* out_cycles_ns_host);
 
 /* ---- general convolution for the ResNet-50-FPN backbone (detectron2 build_retinanet_resnet_fpn_backbone,
  *      call sites probabilistic_retinanet.py:96-101) -------------------------------------------------------------------
@@ -268,6 +271,14 @@ int pod_conv3x3_simt(const float* in, int NB, int H, int W, int Cin, const float
  * ((g_0 + g_1) + ...) / samples, scaled by *scale_dev (or `scale` when scale_dev is NULL). */
 int pod_q1_finish(const float* acc, int n_maps, int groups, int64_t n, int samples, float scale, const float* scale_dev,
                   void* dst_hi, void* dst_lo, void* stream);
+
+/* Streaming form of the same mean (the default, measured faster than the epilogue accumulation: DESIGN.md 3.7): the last
+ * tower layer writes its per-sample split pairs as usual (images x samples x passes maps of n elements) and this kernel
+ * reads them once: for every pass in `mask`, ((x_0 + x_0) + x_1 + ... + x_{live[p]-1}) / samples -> split pair map
+ * image * n_acc + a of dst.  HBM-bound. */
+int pod_q1_mean_act(const void* in_hi, const void* in_lo, int images, int samples, int passes, int mask,
+                    const int* live_host, int64_t n, float scale, const float* scale_dev, void* dst_hi, void* dst_lo,
+                    void* stream);
 
 /* ---- per-anchor sample statistics (probabilistic_inference.py:214-270, quirk Q1) -------------
  * x (B, S, n) fp32 -> out (B, n):  ((x0 + x0) + x1 + ... + x_{S-2}) / S  in that fp32 order
@@ -391,6 +402,7 @@ typedef struct pod_merge_args {
   int* out_classes;
   float* out_probs;
   int* out_count;
+  int* seed_scratch;   /* (B, runs*max_dets) ints: seed list handed from the clustering kernel to the statistics kernel */
 } pod_merge_args;
 int pod_cluster_merge(const pod_merge_args* a, void* stream);
 

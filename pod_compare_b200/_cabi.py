@@ -12,12 +12,12 @@ LIB_PATH = os.path.join(_HERE, "libpodb200.so")
 EXPORTS = [
     "pod_last_error", "pod_version", "pod_device_ok", "pod_status",
     "pod_absmax_accumulate", "pod_pow2_scale_from_absmax", "pod_nchw_to_nhwc_split_dev",
-    "pod_conv3x3_tc_set_wait_limit", "pod_conv3x3_tc_debug_fault",
+    "pod_conv3x3_tc_set_wait_limit", "pod_conv3x3_tc_debug_fault", "pod_conv3x3_tc_debug_clock",
     "pod_philox_dropout_mask", "pod_philox_logit_normals", "pod_philox_box_normals",
     "pod_nchw_to_nhwc_split", "pod_nchw_to_nhwc_f32", "pod_pack_conv_weight", "pod_pack_conv_weight_f32",
     "pod_mask_expand_split", "pod_conv3x3_tc", "pod_conv3x3_tc_set_kblock", "pod_conv3x3_tc_set_chunk_taps", "pod_conv3x3_tc_set_chunk_kblocks", "pod_conv3x3_tc_set_pair", "pod_conv3x3_tc_set_halo", "pod_conv3x3_tc_set_wt", "pod_conv3x3_tc_set_trunc_comp", "pod_conv3x3_tc_status",
     "pod_conv3x3_simt", "pod_sample_mean_q1", "pod_scores", "pod_topk_levels", "pod_decode_cov", "pod_nms_fuse",
-    "pod_cluster_merge", "pod_wire_records", "pod_q1_finish",
+    "pod_cluster_merge", "pod_wire_records", "pod_q1_finish", "pod_q1_mean_act",
     "pod_conv_tc_general", "pod_pack_conv_weight_k", "pod_stem_conv7_pool", "pod_upsample2_add", "pod_split_f32",
 ]
 
@@ -74,7 +74,7 @@ class MergeArgs(C.Structure):
     _fields_ = [("det_boxes", C.c_void_p), ("det_cov", C.c_void_p), ("det_probs", C.c_void_p), ("det_classes", C.c_void_p),
                 ("det_count", C.c_void_p), ("B", C.c_int), ("runs", C.c_int), ("max_dets", C.c_int), ("K", C.c_int),
                 ("affinity", C.c_double), ("out_boxes", C.c_void_p), ("out_cov", C.c_void_p), ("out_scores", C.c_void_p),
-                ("out_classes", C.c_void_p), ("out_probs", C.c_void_p), ("out_count", C.c_void_p)]
+                ("out_classes", C.c_void_p), ("out_probs", C.c_void_p), ("out_count", C.c_void_p), ("seed_scratch", C.c_void_p)]
 
 
 class ConvGArgs(C.Structure):
@@ -139,6 +139,7 @@ def load_library():
     lib.pod_status.argtypes = [C.POINTER(C.c_int)]
     lib.pod_conv3x3_tc_set_wait_limit.argtypes = [C.c_longlong]
     lib.pod_conv3x3_tc_debug_fault.argtypes = [C.c_int]
+    lib.pod_conv3x3_tc_debug_clock.argtypes = [C.c_int, C.POINTER(C.c_longlong)]
     lib.pod_absmax_accumulate.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.pod_pow2_scale_from_absmax.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     lib.pod_nchw_to_nhwc_split_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -160,6 +161,8 @@ def load_library():
                                         C.c_void_p]
     lib.pod_upsample2_add.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.pod_split_f32.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pod_q1_mean_act.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int64, C.c_float,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pod_q1_finish.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib

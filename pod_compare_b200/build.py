@@ -19,8 +19,16 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
 
+def _extra_flags():
+    """POD_LO_BITS=<0..10> in the environment rebuilds the library with that many mantissa bits in the lo operands of the
+    fp16 split (csrc/common.cuh; default 7) -- for the accuracy / power experiments only."""
+    v = os.environ.get("POD_LO_BITS")
+    return ["-DPOD_LO_BITS=%d" % int(v)] if v not in (None, "") else []
+
+
 def _digest():
     h = hashlib.sha256()
+    h.update(" ".join(_extra_flags()).encode())
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
     files.append(os.path.join(os.path.dirname(HERE), "include", "podb200.h"))
     files.append(os.path.abspath(__file__))
@@ -66,7 +74,7 @@ def _build_locked(dig, verbose):
     procs = []
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc_path()] + NVCC_FLAGS + _extra_flags() + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

@@ -130,10 +130,27 @@ __device__ __forceinline__ void pod_box_muller(uint32_t wa, uint32_t wb, float& 
   n1 = r * s;
 }
 
-// fp16 split of x*scale: hi = rn(x*scale), lo = rn(x*scale - hi)
+// fp16 split of x*scale: hi = rn(x*scale), lo = rn(x*scale - hi), with lo rounded to POD_LO_BITS mantissa bits.
+// hi carries 11 significant bits and lo continues them, so the pair holds 12 + POD_LO_BITS + 1 significant bits: 20 at
+// the default of 7 -- a representation error of 2^-21 (4.8e-7 max, 2.8e-7 rms per element), below the 1.4e-6 rms the
+// tensor core's truncating accumulation leaves in a convolution anyway.  Why not all 10 bits: the tower kernel is
+// power-bound and the multipliers' energy depends on the operand bits -- measured with
+// tools/tower_clock_probe.py at the 1 kW cap: 34.9 ms per P3 launch with 10 lo mantissa bits, 33.9 with 5, 32.6 with
+// 0, 30.8 with lo = 0 (profiles/r2b_lo_bits.txt).  Low-order bits that no tolerance can see were costing clock.
+#ifndef POD_LO_BITS
+#define POD_LO_BITS 7
+#endif
+__device__ __forceinline__ __half pod_round_lo(__half lo) {
+  if (POD_LO_BITS >= 10) return lo;
+  constexpr unsigned DROP = 10 - (POD_LO_BITS < 10 ? POD_LO_BITS : 10);
+  // round-to-nearest (ties away) on the magnitude bits; a carry out of the mantissa correctly bumps the exponent
+  const unsigned short b = __half_as_ushort(lo);
+  const unsigned short r = (unsigned short)(((b & 0x7FFFu) + (1u << (DROP - 1))) & ~((1u << DROP) - 1u)) | (b & 0x8000u);
+  return __ushort_as_half(r);
+}
 __device__ __forceinline__ void pod_split_h(float xs, __half& hi, __half& lo) {
   hi = __float2half_rn(xs);
-  lo = __float2half_rn(xs - __half2float(hi));
+  lo = pod_round_lo(__float2half_rn(xs - __half2float(hi)));
 }
 
 // 1/(1-p) as torch computes the dropout scale: fp32(1) / fp32(1-p)

@@ -54,6 +54,7 @@ struct Params {
   int Cout, Cout_pad;
   int relu;
   int dbg_skip_ld;      // debug: skip the TMEM drains (results invalid) to attribute chunk overhead
+  long long* dbg_clock; // debug (POD_TC_DEBUG_CLOCK): CTA 0 of the pair kernel records {clock64, globaltimer} at start and end
   int dbg_no_rmw;       // debug: Q1 accumulation stores without reading back (results invalid) to attribute its cost
   int dbg_fault;        // fault injection (tests): CTA 0's producer never issues its first load -> bounded waits expire
   const float* in_scale_dev;   // optional device-resident input scale (overrides the host value folded into acc_scale)
@@ -929,6 +930,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
   const int tiles_per_map = P.tiles_x * P.tiles_y;
   const int num_pairs = P.q1_mode ? P.q1_num_pairs : (P.num_tiles + 1) >> 1;
   const int pair0 = (int)cluster_id_x(), pair_step = (int)nclusters_x();
+  if (P.dbg_clock != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    P.dbg_clock[0] = clock64();
+    P.dbg_clock[1] = (long long)gt;
+  }
 
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -1122,6 +1129,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
 
   tcgen05_fence_before();
   __syncthreads();
+  if (P.dbg_clock != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    P.dbg_clock[2] = clock64();
+    P.dbg_clock[3] = (long long)gt;
+  }
   cluster_sync_all();                                   // nobody exits while the peer may still signal it
   if (warp == 1) {
     tcgen05_fence_after();
@@ -1526,6 +1539,29 @@ static int g_tc_chunk_kb = 12; // if > 0: K-blocks per accumulation chunk (must 
                                // this is more accurate than 6-K-block chunks without it and 10 % faster
 
 static int g_tc_fault = 0;    // pod_conv3x3_tc_debug_fault
+static long long* g_tc_dbg_clock = nullptr;   // pod_conv3x3_tc_debug_clock: device buffer of 4 words
+
+// Debug / measurement hook: after enabling (out == NULL, enable = 1) CTA 0 of every CTA-pair launch records clock64 and
+// globaltimer at its start and end; a later call with out != NULL copies {cycles, nanoseconds} of the LAST such launch
+// (synchronises).  cycles / ns = the SM clock the kernel really ran at (NVML's sampled clock hides fine-grained throttling).
+extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_debug_clock(int enable, long long* out_cycles_ns_host) {
+  if (out_cycles_ns_host != nullptr) {
+    POD_REQUIRE(g_tc_dbg_clock != nullptr, "pod_conv3x3_tc_debug_clock: not enabled");
+    long long h[4];
+    POD_CUDA(cudaMemcpy(h, g_tc_dbg_clock, sizeof(h), cudaMemcpyDeviceToHost));
+    out_cycles_ns_host[0] = h[2] - h[0];
+    out_cycles_ns_host[1] = h[3] - h[1];
+    return 0;
+  }
+  if (enable && g_tc_dbg_clock == nullptr) {
+    POD_CUDA(cudaMalloc(&g_tc_dbg_clock, 4 * sizeof(long long)));
+    POD_CUDA(cudaMemset(g_tc_dbg_clock, 0, 4 * sizeof(long long)));
+  } else if (!enable && g_tc_dbg_clock != nullptr) {
+    POD_CUDA(cudaFree(g_tc_dbg_clock));
+    g_tc_dbg_clock = nullptr;
+  }
+  return 0;
+}
 
 extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_wait_limit(long long cycles) {
   if (cycles <= 0) cycles = tc::WAIT_LIMIT_CYCLES;
@@ -1670,6 +1706,7 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   if (g_tc_chunk_kb > 0 && (9 * (a->Cin / BK)) % g_tc_chunk_kb == 0) P.kb_per_chunk = g_tc_chunk_kb;
   P.dbg_skip_ld = getenv("POD_TC_DEBUG_SKIP_LD") ? 1 : 0;
   P.dbg_no_rmw = getenv("POD_TC_DEBUG_NO_RMW") ? 1 : 0;
+  P.dbg_clock = g_tc_dbg_clock;
   P.dbg_fault = g_tc_fault;
   P.in_scale_dev = a->in_scale_dev;
   P.acc_scale = 1.0f / ((a->in_scale_dev ? 1.0f : a->in_scale) * a->w_scale) *

@@ -1,4 +1,5 @@
-// Post-NMS merging of per-run detections (MC-dropout samples or ensemble members), one CTA per image.
+// Post-NMS merging of per-run detections (MC-dropout samples or ensemble members): a sequential seed-selection kernel (one
+// CTA per image) followed by a machine-wide statistics kernel (one warp per cluster).
 // Replaces /root/reference/src/probabilistic_inference/inference_utils.py:165-266
 // (general_black_box_ensembles_post_processing up to its final NMS, which pod_nms_fuse then performs):
 //   * all runs of an image are concatenated run-major,
@@ -33,20 +34,21 @@ __device__ __forceinline__ float wsum_f(float v) {
   return v;
 }
 
-__global__ void __launch_bounds__(NT) k_cluster_merge(pod_merge_args a) {
-  extern __shared__ unsigned char smem_raw[];
-  const int cap = a.runs * a.max_dets;
-  float4* s_box = reinterpret_cast<float4*>(smem_raw);
-  float* s_area = reinterpret_cast<float*>(s_box + cap);
-  int* s_cls = reinterpret_cast<int*>(s_area + cap);
-  int* s_row = s_cls + cap;          // row of the per-run arrays this concatenated index came from
-  int* s_seed = s_row + cap;
-  unsigned char* s_assigned = reinterpret_cast<unsigned char*>(s_seed + cap);
-  __shared__ int s_off[65];
-  __shared__ int s_nclusters;
+// Shared by both phases: the runs of image b concatenated run-major into shared memory.
+struct Concat {
+  float4* box;
+  float* area;
+  int* cls;
+  int* row;          // row of the per-run arrays this concatenated index came from
+};
 
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float aff = (float)a.affinity;
+__device__ __forceinline__ int load_concat(const pod_merge_args& a, int b, unsigned char* smem_raw, int* s_off, Concat& c, int nthreads) {
+  const int cap = a.runs * a.max_dets;
+  c.box = reinterpret_cast<float4*>(smem_raw);
+  c.area = reinterpret_cast<float*>(c.box + cap);
+  c.cls = reinterpret_cast<int*>(c.area + cap);
+  c.row = c.cls + cap;
+  const int tid = threadIdx.x;
   if (tid == 0) {
     int n = 0;
     for (int r = 0; r < a.runs; ++r) {
@@ -54,47 +56,79 @@ __global__ void __launch_bounds__(NT) k_cluster_merge(pod_merge_args a) {
       n += a.det_count[b * a.runs + r];
     }
     s_off[a.runs] = n;
-    s_nclusters = 0;
   }
   __syncthreads();
-  const int n = s_off[a.runs];
   for (int r = 0; r < a.runs; ++r) {
     const int cnt = s_off[r + 1] - s_off[r];
-    for (int i = tid; i < cnt; i += NT) {
+    for (int i = tid; i < cnt; i += nthreads) {
       const int row = (b * a.runs + r) * a.max_dets + i;
       const float4 q = reinterpret_cast<const float4*>(a.det_boxes)[row];
       const int j = s_off[r] + i;
-      s_box[j] = q;
-      s_area[j] = area_of(q);
-      s_cls[j] = a.det_classes[row];
-      s_row[j] = row;
-      s_assigned[j] = 0;
+      c.box[j] = q;
+      c.area[j] = area_of(q);
+      c.cls[j] = a.det_classes[row];
+      c.row[j] = row;
     }
   }
   __syncthreads();
+  return s_off[a.runs];
+}
 
-  // ---- sequential clustering (inference_utils.py:202-215) ----
+// ---- phase 1: sequential clustering (inference_utils.py:202-215), one CTA of 1024 threads per image.  The only
+// sequential part of the merge: box i seeds a cluster unless an earlier seed already claimed it.  Writes the seed list.
+constexpr int NT_SEED = 1024;
+__global__ void __launch_bounds__(NT_SEED) k_cluster_seeds(pod_merge_args a) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ int s_off[65];
+  __shared__ int s_nclusters;
+  const int cap = a.runs * a.max_dets;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  Concat c;
+  const int n = load_concat(a, b, smem_raw, s_off, c, NT_SEED);
+  unsigned char* s_assigned = reinterpret_cast<unsigned char*>(c.row + cap);
+  for (int j = tid; j < n; j += NT_SEED) s_assigned[j] = 0;
+  if (tid == 0) s_nclusters = 0;
+  __syncthreads();
+  const float aff = (float)a.affinity;
+  int* seeds = a.seed_scratch + (int64_t)b * cap;
   for (int i = 0; i < n; ++i) {
     if (s_assigned[i]) continue;                       // uniform: read after the barrier below
-    const float4 bi = s_box[i];
-    const float ai = s_area[i];
-    const int ci = s_cls[i];
+    const float4 bi = c.box[i];
+    const float ai = c.area[i];
+    const int ci = c.cls[i];
     __syncthreads();                                   // everyone has read assigned[i] before it may change
-    for (int j = tid; j < n; j += NT)
-      if (s_cls[j] == ci && iou_d2(bi, ai, s_box[j], s_area[j]) >= aff) s_assigned[j] = 1;
-    if (tid == 0) s_seed[s_nclusters++] = i;
+    for (int j = tid; j < n; j += NT_SEED)
+      if (c.cls[j] == ci && iou_d2(bi, ai, c.box[j], c.area[j]) >= aff) s_assigned[j] = 1;
+    if (tid == 0) seeds[s_nclusters++] = i;
     __syncthreads();
   }
   __syncthreads();
-  const int nc = s_nclusters;
+  if (tid == 0) a.out_count[b] = s_nclusters;
+}
 
-  // ---- cluster statistics (inference_utils.py:223-247), one warp per cluster ----
+// ---- phase 2: cluster statistics (inference_utils.py:223-247), one warp per cluster, gridDim.y CTAs per image ----
+__global__ void __launch_bounds__(NT) k_cluster_merge(pod_merge_args a) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ int s_off[65];
+  const int cap = a.runs * a.max_dets;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float aff = (float)a.affinity;
+  const int nc = a.out_count[b];
+  if ((int)blockIdx.y * (NT / 32) >= nc) return;       // uniform per CTA: nothing to do
+  Concat cc_;
+  const int n = load_concat(a, b, smem_raw, s_off, cc_, NT);
+  float4* s_box = cc_.box;
+  float* s_area = cc_.area;
+  int* s_cls = cc_.cls;
+  int* s_row = cc_.row;
+  const int* s_seed = a.seed_scratch + (int64_t)b * cap;
+
   float* o_boxes = a.out_boxes + (int64_t)b * cap * 4;
   float* o_cov = a.out_cov + (int64_t)b * cap * 16;
   float* o_scores = a.out_scores + (int64_t)b * cap;
   int* o_classes = a.out_classes + (int64_t)b * cap;
   float* o_probs = a.out_probs + (int64_t)b * cap * a.K;
-  for (int c = warp; c < nc; c += NT / 32) {
+  for (int c = blockIdx.y * (NT / 32) + warp; c < nc; c += gridDim.y * (NT / 32)) {
     const int i = s_seed[c];
     const float4 bi = s_box[i];
     const float ai = s_area[i];
@@ -159,7 +193,6 @@ __global__ void __launch_bounds__(NT) k_cluster_merge(pod_merge_args a) {
       o_classes[c] = bestk;
     }
   }
-  if (tid == 0) a.out_count[b] = nc;
 }
 }  // namespace
 
@@ -171,14 +204,24 @@ extern "C" __attribute__((visibility("default"))) int pod_cluster_merge(const po
   POD_REQUIRE(a->B > 0 && a->runs > 0 && a->runs <= 64 && a->max_dets > 0 && a->K > 0, "pod_cluster_merge: bad shape (runs <= 64)");
   const int cap = a->runs * a->max_dets;
   POD_REQUIRE(cap <= 8192, "pod_cluster_merge: runs*max_dets must be <= 8192");
-  const size_t smem = (size_t)cap * (16 + 4 + 4 + 4 + 4 + 1) + 16;
+  POD_REQUIRE(a->seed_scratch, "pod_cluster_merge: seed_scratch (B x runs*max_dets ints) is required");
+  const size_t smem = (size_t)cap * (16 + 4 + 4 + 4 + 1) + 16;
   POD_REQUIRE(smem <= 200 * 1024, "pod_cluster_merge: too many detections for shared memory");
   static size_t configured = 0;
   if (smem > configured) {
+    POD_CUDA(cudaFuncSetAttribute(k_cluster_seeds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     POD_CUDA(cudaFuncSetAttribute(k_cluster_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  k_cluster_merge<<<a->B, NT, smem, (cudaStream_t)stream>>>(*a);
+  // phase 1: the sequential seed selection (one CTA per image); phase 2: per-cluster statistics, one warp per cluster,
+  // spread over enough CTAs per image to fill the machine (the single-CTA form spent 44 ms per 3000 detections)
+  k_cluster_seeds<<<a->B, NT_SEED, smem, (cudaStream_t)stream>>>(*a);
+  POD_LAUNCH_CHECK();
+  int per_image = (2 * pod_num_sms() + a->B - 1) / a->B;
+  const int max_useful = (cap + NT / 32 - 1) / (NT / 32);
+  if (per_image > max_useful) per_image = max_useful;
+  if (per_image < 1) per_image = 1;
+  k_cluster_merge<<<dim3(a->B, per_image), NT, smem, (cudaStream_t)stream>>>(*a);
   POD_LAUNCH_CHECK();
   return 0;
 }

@@ -281,6 +281,99 @@ k_q1_finish(const float* __restrict__ acc, int64_t oct_per_map, int64_t total, i
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Q1 sample mean of the last tower layer, streaming form: reads the per-sample split-pair maps the tower kernel wrote
+// (images x samples x passes, sample-major / pass-minor) and writes, for every pass whose bit is set in `mask`, the
+// reference's weighted mean ((x_0 + x_0) + x_1 + ... + x_{L-1}) / S  (probabilistic_inference.py:214-270) as a split
+// pair: the operand of the (linear) output convolutions cls_score / cls_var / bbox_cov, which then run once per image.
+// HBM-bound: S - 1 maps read per map written; 8 channels per thread, eight samples in flight.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_q1_mean_act(const __half* __restrict__ hi, const __half* __restrict__ lo, int64_t oct_per_map, int64_t total, int S, int passes, int mask,
+              int live0, int live1, float scale, const float* __restrict__ scale_dev, __half* __restrict__ ohi, __half* __restrict__ olo) {
+  if (scale_dev != nullptr) scale = __ldg(scale_dev);
+  const float inv_scale = 1.0f / scale;                 // power of two: exact
+  const int n_acc = __popc(mask);
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o8 = t % oct_per_map;
+    const int64_t m = t / oct_per_map;                  // output map = image * n_acc + a
+    const int a = (int)(m % n_acc);
+    const int64_t b = m / n_acc;
+    int p = 0;
+    for (int k = 0, seen = 0; k < passes; ++k)
+      if ((mask >> k) & 1) { if (seen == a) p = k; ++seen; }
+    const int L = p == 0 ? live0 : live1;
+    const uint4* ph = reinterpret_cast<const uint4*>(hi) + (b * S * passes + p) * oct_per_map + o8;
+    const uint4* pl = reinterpret_cast<const uint4*>(lo) + (b * S * passes + p) * oct_per_map + o8;
+    const int64_t step = (int64_t)passes * oct_per_map;
+    float acc[8];
+    auto unpack = [&](const uint4 h, const uint4 l, float (&v)[8]) {
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+        const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
+        v[2 * i] = __fadd_rn(hf.x, lf.x) * inv_scale;
+        v[2 * i + 1] = __fadd_rn(hf.y, lf.y) * inv_scale;
+      }
+    };
+    {
+      float v[8];
+      unpack(__ldcs(ph), __ldcs(pl), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = __fadd_rn(v[i], v[i]);        // sample 0 enters the reference's sum twice (quirk Q1)
+    }
+    int s = 1;
+    for (; s + 8 <= L; s += 8) {                        // eight samples (sixteen 16-byte loads) in flight per thread
+      uint4 h[8], l[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { h[u] = __ldcs(ph + (s + u) * step); l[u] = __ldcs(pl + (s + u) * step); }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float v[8];
+        unpack(h[u], l[u], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = __fadd_rn(acc[i], v[i]);
+      }
+    }
+    for (; s < L; ++s) {
+      float v[8];
+      unpack(__ldcs(ph + s * step), __ldcs(pl + s * step), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = __fadd_rn(acc[i], v[i]);
+    }
+    uint32_t qh[4], ql[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half h0, l0, h1, l1;
+      pod_split_h(__fdiv_rn(acc[2 * i], (float)S) * scale, h0, l0);
+      pod_split_h(__fdiv_rn(acc[2 * i + 1], (float)S) * scale, h1, l1);
+      qh[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      ql[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    reinterpret_cast<uint4*>(ohi)[t] = make_uint4(qh[0], qh[1], qh[2], qh[3]);
+    reinterpret_cast<uint4*>(olo)[t] = make_uint4(ql[0], ql[1], ql[2], ql[3]);
+  }
+}
+
+extern "C" __attribute__((visibility("default"))) int pod_q1_mean_act(const void* in_hi, const void* in_lo, int images, int samples, int passes, int mask,
+                                                        const int* live /* host, per pass */, int64_t n, float scale, const float* scale_dev,
+                                                        void* dst_hi, void* dst_lo, void* stream) {
+  POD_REQUIRE(in_hi && in_lo && dst_hi && dst_lo && live && images > 0 && samples > 1 && (passes == 1 || passes == 2), "pod_q1_mean_act: bad args");
+  POD_REQUIRE(mask > 0 && mask < (1 << passes) && n > 0 && n % 8 == 0 && (scale > 0.f || scale_dev), "pod_q1_mean_act: bad mask / size (n%%8)");
+  for (int p = 0; p < passes; ++p)
+    POD_REQUIRE(!((mask >> p) & 1) || (live[p] >= 1 && live[p] <= samples), "pod_q1_mean_act: live[%d] out of range", p);
+  POD_REQUIRE(((uintptr_t)in_hi | (uintptr_t)in_lo | (uintptr_t)dst_hi | (uintptr_t)dst_lo) % 16 == 0, "pod_q1_mean_act: 16-byte alignment");
+  const int n_acc = __builtin_popcount(mask);
+  const int64_t opm = n / 8, total = opm * images * n_acc;
+  const int64_t want = (total + 255) / 256, cap = (int64_t)pod_num_sms() * 6;
+  k_q1_mean_act<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>((const __half*)in_hi, (const __half*)in_lo, opm, total, samples,
+                                                                                 passes, mask, live[0], passes > 1 ? live[1] : 0, scale, scale_dev,
+                                                                                 (__half*)dst_hi, (__half*)dst_lo);
+  POD_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" __attribute__((visibility("default"))) int pod_q1_finish(const float* acc, int n_maps, int groups, int64_t n, int samples, float scale,
                                                       const float* scale_dev, void* dst_hi, void* dst_lo, void* stream) {
   POD_REQUIRE(acc && dst_hi && dst_lo && n_maps > 0 && groups > 0 && n > 0 && n % 8 == 0 && samples > 0, "pod_q1_finish: bad args (n%%8)");

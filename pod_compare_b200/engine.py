@@ -192,11 +192,13 @@ class HeadEngine:
         """MC-dropout head loop: feats = list over levels of (B,256,H,W) fp32.
         Returns raw per-sample outputs, each (B, N, R, D).
 
-        fuse_q1 (pre-NMS aggregation only, implies skip_unread): the reference's sample "mean" of box_cls, box_cls_var
+        fuse_q1 ("stream" | True, or "epilogue"; pre-NMS aggregation only, implies skip_unread): the reference's sample "mean" of box_cls, box_cls_var
         and box_reg_var (probabilistic_inference.py:214-270) is a fixed linear combination of the samples, and cls_score /
         cls_var / bbox_cov are linear (a 3x3 convolution plus bias; the weights sum to one), so
             mean_s head(x_s) = head(mean_s x_s).
-        The last tower layer then accumulates (2 x_0 + x_1 + ... + x_{N-2}) in its epilogue instead of writing N maps,
+        The mean activation (2 x_0 + x_1 + ... + x_{N-2}) / N of the last tower layer is formed either by one streaming
+        pass over the per-sample maps ("stream", default) or inside the tcgen05 epilogue ("epilogue": nothing per
+        sample is written, but the read-back of the running sums costs more than the streaming pass),
         and each of those three output convolutions runs ONCE per image: 3 + N output convolutions per location instead
         of 4N - 3, and no per-sample logits / variances are ever written (returned with a sample dimension of 1: they
         ARE the Q1 means).  Only box_delta stays per sample: every sample's decoded box enters the epistemic
@@ -220,6 +222,7 @@ class HeadEngine:
         passes = 2 if (pc.cls_var or pc.bbox_cov) else 1
         dev = self.device
         fuse = bool(fuse_q1) and n_mc > 1
+        in_epilogue = fuse and fuse_q1 == "epilogue"       # accumulate inside the tcgen05 epilogue (slower: DESIGN.md 3.7)
         if fuse:
             skip_unread = True
         n_stat = 1 if fuse else n_mc                     # sample dimension of the outputs that are only ever averaged
@@ -230,7 +233,8 @@ class HeadEngine:
         max_hw = max(h * wd for h, wd in level_hw)
         groups = (n_mc + Q1_GROUP - 1) // Q1_GROUP
         if fuse:
-            q1_acc = self._get("q1_acc", B * 2 * groups * max_hw * 256, torch.float32)
+            if in_epilogue:
+                q1_acc = self._get("q1_acc", B * 2 * groups * max_hw * 256, torch.float32)
             q1_mean = (self._get("q1m_hi", B * 2 * max_hw * 256, torch.float16), self._get("q1m_lo", B * 2 * max_hw * 256, torch.float16))
         nmaps = B * n_mc * passes
         act = [(self._get("a%d_hi" % i, nmaps * max_hw * 256, torch.float16),
@@ -267,8 +271,8 @@ class HeadEngine:
                 n_acc = bin(acc_mask).count("1")
                 for layer in range(1, len(tw)):
                     d = ops.make_dropout(pc.dropout_rate, seed, image0, n_mc, t_passes, 0, tower, layer, lvl)
-                    if acc_mask and layer == len(tw) - 1:
-                        q1_live = [n_mc - 1, n_mc - 1] if tower == TOWER_CLS else [n_mc, n_mc - 1]
+                    q1_live = [n_mc - 1, n_mc - 1] if tower == TOWER_CLS else [n_mc, n_mc - 1]
+                    if acc_mask and layer == len(tw) - 1 and in_epilogue:
                         ops.conv3x3_tc(act[cur][0], act[cur][1], 1.0, NB, H, W, 256, tw[layer].w_hi, tw[layer].w_lo,
                                        tw[layer].w_scale, tw[layer].bias, 256, 256, POD_OUT_HIDDEN, True,
                                        out_hi=act[cur ^ 1][0], out_lo=act[cur ^ 1][1], out_scale=1.0, drop=d,
@@ -279,6 +283,10 @@ class HeadEngine:
                     else:
                         self._conv_hidden(act[cur], NB, H, W, tw[layer], act[cur ^ 1], d, fscale, map_group=grp, map_live=live,
                                           tag="tower256" if not self.profile_layers else "tower256_L%d" % layer)
+                        if acc_mask and layer == len(tw) - 1:
+                            # streaming form (default): the per-sample maps just written are averaged by one HBM-bound pass
+                            ops.q1_mean_act(act[cur ^ 1][0], act[cur ^ 1][1], B, n_mc, t_passes, acc_mask, q1_live[:t_passes],
+                                            HW * 256, fscale, q1_mean[0], q1_mean[1])
                     cur ^= 1
                 n_live = n_mc - 1 if (skip_unread and n_mc > 1) else n_mc        # samples whose mean/var heads are read
                 # output convs: pass-0 maps feed the mean head, pass-1 maps the variance head (Q2)

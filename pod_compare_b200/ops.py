@@ -264,6 +264,18 @@ def set_conv_debug_fault(on):
     check(_cabi.load_library().pod_conv3x3_tc_debug_fault(int(bool(on))), "pod_conv3x3_tc_debug_fault")
 
 
+def conv_debug_clock(enable=None):
+    """enable=True/False switches the in-kernel clock probe of the CTA-pair kernel; enable=None returns
+    (cycles, ns, MHz) of the last CTA-pair launch."""
+    lib = _cabi.require_device()
+    if enable is not None:
+        check(lib.pod_conv3x3_tc_debug_clock(int(bool(enable)), None), "pod_conv3x3_tc_debug_clock")
+        return None
+    out = (C.c_longlong * 2)()
+    check(lib.pod_conv3x3_tc_debug_clock(0, out), "pod_conv3x3_tc_debug_clock")
+    return out[0], out[1], (1e3 * out[0] / out[1]) if out[1] else float("nan")
+
+
 def set_conv_kblock(bk):
     check(_cabi.load_library().pod_conv3x3_tc_set_kblock(int(bk)), "pod_conv3x3_tc_set_kblock")
 
@@ -473,8 +485,10 @@ def cluster_merge(det, runs, affinity):
     a.affinity = float(affinity)
     a.out_boxes, a.out_cov, a.out_scores = out["boxes"].data_ptr(), out["cov"].data_ptr(), out["scores"].data_ptr()
     a.out_classes, a.out_probs, a.out_count = out["classes"].data_ptr(), out["probs"].data_ptr(), out["count"].data_ptr()
+    seeds = torch.empty((B, cap), dtype=torch.int32, device=dev)
+    a.seed_scratch = seeds.data_ptr()
     check(lib.pod_cluster_merge(C.byref(a), stream_ptr()), "pod_cluster_merge")
-    _count()
+    _count(2)
     return out
 
 
@@ -596,3 +610,20 @@ def split_f32(x, scale=1.0, scale_dev=None, relu=False, out_hi=None, out_lo=None
           "pod_split_f32")
     _count()
     return out_hi, out_lo
+
+
+def q1_mean_act(act_hi, act_lo, images, samples, passes, mask, live, n, scale_dev, out_hi, out_lo):
+    """Per-sample split-pair maps of the last tower layer -> Q1-weighted mean maps of the passes in `mask` (pod_q1_mean_act)."""
+    lib = _cabi.require_device()
+    n_acc = bin(mask).count("1")
+    assert act_hi.numel() >= images * samples * passes * n and out_hi.numel() >= images * n_acc * n
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(lib.pod_q1_mean_act(ptr(act_hi), ptr(act_lo), int(images), int(samples), int(passes), int(mask), int_array(list(live) + [0]),
+                              int(n), 1.0, ptr(scale_dev), ptr(out_hi), ptr(out_lo), stream_ptr()), "pod_q1_mean_act")
+    if PROFILE is not None:
+        e1.record()
+        reads = sum(int(live[p]) for p in range(passes) if (mask >> p) & 1)
+        PROFILE.append((e0, e1, 4.0 * images * n * (reads + n_acc), "act_mean"))       # bytes: split pairs read + written
+    _count()

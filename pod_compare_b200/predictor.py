@@ -82,9 +82,10 @@ class ProbabilisticPredictor:
         # only those outputs are left out.  Results are unchanged; set False to evaluate them anyway.
         self.skip_unread_outputs = True
         # Pre-NMS MC-dropout aggregation: the sample "mean" of box_cls / box_cls_var / box_reg_var commutes with the linear
-        # output convolutions, so the last tower layer accumulates the reference's weighted sample sum in its epilogue and
-        # cls_score / cls_var / bbox_cov run once per image (engine.HeadEngine.head_mc fuse_q1).  Needs skip_unread_outputs;
-        # set False to evaluate and average every sample's outputs as the reference does.
+        # output convolutions, so the reference's weighted sample mean is taken of the LAST TOWER LAYER and cls_score /
+        # cls_var / bbox_cov run once per image (engine.HeadEngine.head_mc fuse_q1).  True / "stream": one HBM-bound pass
+        # over the per-sample maps (default); "epilogue": accumulated inside the tcgen05 epilogue (slower).
+        # Needs skip_unread_outputs; False evaluates and averages every sample's outputs as the reference does.
         self.fuse_sample_mean = True
         self.max_activation_bytes = 64e9  # auto-chunking budget of infer_from_features / predict_batch
         self._copy_stream = None          # host->device prefetch of the next chunk (infer_from_features chunk_images)
@@ -220,8 +221,112 @@ class ProbabilisticPredictor:
             return res, det
         return self.infer_from_features(feats, hw[0], out_hw[0], image0=image0)
 
+    def infer_from_images(self, images, out_hw=None, image0=0, seed=None, chunk_images=None, return_det=False):
+        """images: (B, 3, H, W) uint8 / float tensor (host or device) of raw frames in the model's channel order.
+        Backbone(s) + head path per chunk of `chunk_images` images (host frames of chunk i+1 are uploaded on the copy
+        stream while chunk i computes).  The per-image entry `predictor(input_im)` and `predict_batch` end up here too."""
+        if self.backbone is None:
+            raise _cabi.PodError("predictor.backbone is not set: load_backbone(state_dict) first")
+        B, _, H, W = images.shape
+        chunk = int(chunk_images) if chunk_images else B
+        main = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+
+        def stage(c0, c1):
+            if images.is_cuda:
+                return images[c0:c1], None
+            with torch.cuda.stream(self._copy_stream):
+                dev = images[c0:c1].to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            dev.record_stream(main)
+            return dev, ev
+
+        bounds = [(c0, min(B, c0 + chunk)) for c0 in range(0, B, chunk)]
+        res, dets = [], []
+        nxt = stage(*bounds[0])
+        for i, (c0, c1) in enumerate(bounds):
+            cur, ev = nxt
+            if i + 1 < len(bounds):
+                nxt = stage(*bounds[i + 1])
+            if ev is not None:
+                main.wait_event(ev)
+            if self.inference_mode == 'ensembles' and self.member_backbones is not None:
+                feats = [net(cur) for net in self.member_backbones]      # every member sees its own feature maps
+            else:
+                feats = self.backbone(cur)
+            out = self.infer_from_features(feats, (H, W), out_hw or (H, W), image0=image0 + c0, seed=seed, return_candidates=True)
+            res.extend(out[0])
+            dets.append(out[3])
+        if not return_det:
+            return res
+        det = {k: (torch.cat([d[k] for d in dets], 0) if isinstance(v, torch.Tensor) else v) for k, v in dets[0].items()}
+        return res, det
+
+    def capture(self, example, out_hw=None, image0=0, seed=None):
+        """CUDA-graph the whole call for a fixed input shape (launch-bound small batches: a single-forward batch of 8 is
+        ~250 kernel launches of a few tens of microseconds each, and the Python / ctypes / tensor-map-encode cost per
+        launch is of the same order).  `example` is a (B,3,H,W) frame tensor (backbone + head) or a list of FPN maps.
+        Returns run(new_input, image_ids=None) -> (list of Instances, det dict); new inputs are copied into the captured
+        buffers, the graph is replayed, and only the final count read-back + pod_status check happen on the host.
+        The noise streams are keyed by image0 + position (fixed at capture), exactly as in the eager call."""
+        from_images = isinstance(example, torch.Tensor)
+        if from_images and self.backbone is None:
+            raise _cabi.PodError("predictor.backbone is not set: load_backbone(state_dict) first")
+        if from_images:
+            static_in = example.to(self.device).contiguous().clone()
+            H, W = int(static_in.shape[-2]), int(static_in.shape[-1])
+        else:
+            static_in = [f.to(self.device, dtype=torch.float32).contiguous().clone() for f in example]
+            if out_hw is None:
+                raise ValueError("capture(features) needs out_hw / image size")
+            H, W = out_hw
+        out_hw = tuple(out_hw) if out_hw is not None else (H, W)
+
+        def forward():
+            if from_images:
+                if self.inference_mode == 'ensembles' and self.member_backbones is not None:
+                    feats = [net(static_in) for net in self.member_backbones]
+                else:
+                    feats = self.backbone(static_in)
+            else:
+                feats = static_in
+            return self._forward_det(feats, (H, W), out_hw, image0, seed)
+
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):                       # warm-up: one-off attribute calls, buffer growth, lazy init
+            forward()
+            forward()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        ops.check_status()
+        graph = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
+        with torch.cuda.graph(graph):
+            det = forward()
+        launches = ops.launch_count() - n0                  # kernels of this library inside one replay
+
+        def run(new_input):
+            if from_images:
+                static_in.copy_(new_input, non_blocking=True)
+            else:
+                for dst, src in zip(static_in, new_input):
+                    dst.copy_(src, non_blocking=True)
+            graph.replay()
+            ops._count(launches)
+            return self._to_instances(det, out_hw), det
+        run.graph, run.launches = graph, launches
+        return run
+
+    def _forward_det(self, feats, image_hw, out_hw, image0, seed):
+        """Device-only part of infer_from_features (no host synchronisation): features -> detection buffers."""
+        out = self.infer_from_features(feats, image_hw, out_hw, image0=image0, seed=seed, return_candidates=True, _no_host=True)
+        return out
+
     def infer_from_features(self, feats, image_hw, out_hw=None, image0=0, seed=None, return_raw=False,
-                            return_candidates=False, chunk_images=None):
+                            return_candidates=False, chunk_images=None, _no_host=False):
         """feats: list over FPN levels of (B,256,Hl,Wl) fp32 tensors (host or device).
         image_hw: size of the network input (Instances.image_size before rescale,
         inference_utils.py:39-41); out_hw: requested output resolution (:374-397).
@@ -239,7 +344,7 @@ class ProbabilisticPredictor:
             raise _cabi.PodError("got %d feature sets for %d ensemble members" % (len(feats), len(self.weight_sets)))
         lv0 = feats[0] if per_member else feats
         B = int(lv0[0].shape[0])
-        if chunk_images is None and B > 1:
+        if chunk_images is None and B > 1 and not _no_host:
             # keep the activation working set inside the budget (default 64 GB of the 180 GB): a batch of 64 images at
             # N=30 would otherwise ask for 2 x 64 x 60 maps of 96x160x256 split pairs = 240 GB
             auto = max(1, int(self.max_activation_bytes // self._activation_bytes_per_image(lv0)))
@@ -276,7 +381,8 @@ class ProbabilisticPredictor:
             n_runs = max(1, int(self.num_mc_dropout_runs))
             skip = self.skip_unread_outputs and not post_nms and n_runs > 1
             raw, level_off = eng.head_mc(feats, n_runs, seed, image0, skip_unread=skip,
-                                         fuse_q1=skip and self.fuse_sample_mean and not return_raw)
+                                         fuse_q1=(self.fuse_sample_mean if isinstance(self.fuse_sample_mean, str) else "stream")
+                                         if (skip and self.fuse_sample_mean and not return_raw) else False)
         elif self.mc_dropout_enabled and self.num_mc_dropout_runs > 1:
             raise _cabi.PodError("MC_DROPOUT.ENABLE with DROPOUT_RATE == 0 is not supported")
         else:
@@ -286,6 +392,8 @@ class ProbabilisticPredictor:
         else:
             cand = eng.candidates(raw, level_off, anchors, seed, image0)
             det = eng.detections(cand, {'bayes_od': 1, 'anchor_statistics': 2}.get(mode, 0), image_hw, out_hw)
+        if _no_host:
+            return det                      # CUDA-graph capture: the host-side read-back happens after the replay
         res = self._to_instances(det, out_hw)
         if return_raw or return_candidates:
             return res, (raw if return_raw else None), cand, det

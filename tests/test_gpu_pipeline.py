@@ -6,7 +6,7 @@ checked bit-exactly stage-isolated (identical inputs), and end-to-end on the fix
 margins at those discontinuities are far above the 1e-6 numerical differences of the head.
 BayesOD fuses with fp64 4x4 inverses in-kernel while the reference uses fp32 LAPACK: identical
 inputs are compared to the oracle evaluated in fp64 at 1e-5, and to the fp32 reference fixtures at
-a condition-aware 2e-3.
+the measured envelope of the reference's own fp32 rounding (2e-3 px / 2e-5; profiles/r2a_bayesod_envelope.txt).
 """
 import os
 
@@ -170,9 +170,10 @@ def test_nms_and_bayesod_on_planted_candidates(tag):
             assert np.allclose(det["probs"][0, :n].cpu().numpy(), g[key + "probs"], rtol=1e-5, atol=1e-8), key
             assert np.allclose(det["boxes"][0, :n].cpu().numpy(), r64.boxes.numpy(), rtol=1e-5, atol=1e-3), key
             assert _cov_close(det["cov"][0, :n].cpu().numpy(), r64.cov.numpy(), 1e-5), key
-            # against the fp32 reference fixture (condition-aware tolerance)
-            assert np.allclose(det["boxes"][0, :n].cpu().numpy(), g[key + "boxes"], rtol=1e-4, atol=2e-2), key
-            assert _cov_close(det["cov"][0, :n].cpu().numpy(), g[key + "cov"], 2e-3), key
+            # against the fp32 reference fixture: the measured envelope (profiles/r2a_bayesod_envelope.txt) is 4.9e-4 px /
+            # 1.9e-6, all of it the reference's own fp32-LAPACK rounding (the same distance separates it from fp64)
+            assert np.allclose(det["boxes"][0, :n].cpu().numpy(), g[key + "boxes"], rtol=1e-6, atol=2e-3), key
+            assert _cov_close(det["cov"][0, :n].cpu().numpy(), g[key + "cov"], 2e-5), key
 
 
 def _match_detections(got_boxes, ref_boxes, tol_px):
@@ -346,8 +347,10 @@ def _compare_path(res, cand, det, ref_final, ref_cand, ref_det, pp, bayes, prob_
     assert np.array_equal(res.pred_classes.cpu().numpy()[i_g], ref_final.classes.numpy()[i_r])
     assert _close(res.scores.cpu().numpy()[i_g], ref_final.scores.numpy()[i_r], prob_rtol, prob_atol, "scores")
     assert _close(res.pred_cls_probs.cpu().numpy()[i_g], ref_final.probs.numpy()[i_r], prob_rtol, prob_atol, "probability vectors")
-    assert _close(res.pred_boxes.tensor.cpu().numpy()[i_g], ref_final.boxes.numpy()[i_r], 1e-4, 2e-2 if bayes else 2e-3, "boxes")
-    assert _cov_close(res.pred_boxes_covariance.cpu().numpy()[i_g], ref_final.cov.numpy()[i_r], 2e-3 if bayes else 2e-4)
+    # BayesOD end to end: measured worst case 7.8e-4 px / 1.4e-5 at cond(sum P) = 4e2 (profiles/r2a_bayesod_envelope.txt);
+    # the fused covariance is bounded at the north-star's 1e-4 (scaled by the matrix' largest entry), boxes at 3e-3 px
+    assert _close(res.pred_boxes.tensor.cpu().numpy()[i_g], ref_final.boxes.numpy()[i_r], 1e-4, 3e-3 if bayes else 2e-3, "boxes")
+    assert _cov_close(res.pred_boxes_covariance.cpu().numpy()[i_g], ref_final.cov.numpy()[i_r], 1e-4 if bayes else 2e-4)
     # output order: descending score up to near-ties
     sc = res.scores.cpu().numpy()
     if not bayes or pp.cls_merge == "max_score":
@@ -361,8 +364,8 @@ def _check_final(inst, g, bayes):
     assert np.array_equal(inst.pred_classes.cpu().numpy(), g["final_classes"])
     assert np.allclose(inst.scores.cpu().numpy(), g["final_scores"], rtol=1e-4, atol=1e-7)
     assert np.allclose(inst.pred_cls_probs.cpu().numpy(), g["final_probs"], rtol=1e-4, atol=1e-7)
-    assert np.allclose(inst.pred_boxes.tensor.cpu().numpy(), g["final_boxes"], rtol=1e-4, atol=2e-2 if bayes else 2e-3)
-    assert _cov_close(inst.pred_boxes_covariance.cpu().numpy(), g["final_cov"], 2e-3 if bayes else 2e-4)
+    assert np.allclose(inst.pred_boxes.tensor.cpu().numpy(), g["final_boxes"], rtol=1e-4, atol=3e-3 if bayes else 2e-3)
+    assert _cov_close(inst.pred_boxes_covariance.cpu().numpy(), g["final_cov"], 1e-4 if bayes else 2e-4)
 
 
 @pytest.mark.parametrize("name", [n for n in C.CASES if not C.is_post_nms(n)])
@@ -883,8 +886,9 @@ def test_predict_batch_json_end_to_end():
 
 
 # ------------------------------------------------------------------------------------------ fused Q1 sample accumulation
+@pytest.mark.parametrize("how", ["stream", "epilogue"])
 @pytest.mark.parametrize("name", ["mcdrop_pre_n4", "droponly_pre_n3", "bayesod_mc_n3", "fullcov_mc_n3"])
-def test_fused_sample_mean_equals_per_sample_evaluation(name):
+def test_fused_sample_mean_equals_per_sample_evaluation(name, how):
     """head_mc(fuse_q1): the last tower layer accumulates the reference's weighted sample sum in the conv epilogue and
     cls_score / cls_var / bbox_cov run once per image on the mean activation.  mean_s head(x_s) == head(mean_s x_s) for
     a linear head, so the Q1 means must agree with the per-sample evaluation to fp32 round-off, per-sample deltas must be
@@ -894,10 +898,11 @@ def test_fused_sample_mean_equals_per_sample_evaluation(name):
     feats3 = [torch.cat([f, f * 0.5, f * 1.5], 0) for f in feats]
     pred = build_predictor(cfg)
     pred.load_weight_sets(sds[0])
+    pred.fuse_sample_mean = how
     eng = pred._engine
     dev = [f.cuda().contiguous() for f in feats3]
     out = {}
-    for fuse in (False, True):
+    for fuse in (False, how):
         ops.PROFILE = []
         try:
             raw, level_off = eng.head_mc(dev, n_mc, seed, img, skip_unread=True, fuse_q1=fuse)
@@ -907,7 +912,7 @@ def test_fused_sample_mean_equals_per_sample_evaluation(name):
             ops.PROFILE = None
         assert ops.status() == 0
         out[fuse] = ({k: (v.clone() if v is not None else None) for k, v in raw.items()}, flop)
-    (raw_u, flop_u), (raw_f, flop_f) = out[False], out[True]
+    (raw_u, flop_u), (raw_f, flop_f) = out[False], out[how]
     assert flop_f < flop_u
     assert torch.equal(raw_f["deltas"], raw_u["deltas"])                       # per-sample deltas: same kernels, same bits
     for k in ("logits", "logvar", "regvar"):
@@ -920,7 +925,7 @@ def test_fused_sample_mean_equals_per_sample_evaluation(name):
         scale = float(want.abs().max())
         assert float((got - want).abs().max()) <= 2e-6 * scale, k             # fp32 round-off of a different summation order
     # and end to end against the oracle, through the default (fused) product path
-    assert pred.fuse_sample_mean and pred.skip_unread_outputs
+    assert pred.fuse_sample_mean == how and pred.skip_unread_outputs
     res, _, cand, det = pred.infer_from_features(feats, hw, out_hw, image0=img, seed=seed, return_candidates=True)
     torch.set_num_threads(8)
     ref_final, ref_cand, ref_det = O.predict(feats, [O.unpack_head(sds[0], pp)], pp, mode, hw, out_hw=out_hw, n_mc=n_mc,
@@ -953,10 +958,14 @@ def test_fused_sample_mean_with_more_samples_than_one_group():
     dev = [f.cuda().contiguous() for f in feats]
     raw_u, _ = eng.head_mc(dev, 19, seed, img, skip_unread=True, fuse_q1=False)
     raw_u = {k: v.clone() for k, v in raw_u.items()}
-    raw_f, _ = eng.head_mc(dev, 19, seed, img, skip_unread=True, fuse_q1=True)
+    raw_f, _ = eng.head_mc(dev, 19, seed, img, skip_unread=True, fuse_q1="epilogue")
+    raw_f = {k: v.clone() for k, v in raw_f.items()}
+    raw_s, _ = eng.head_mc(dev, 19, seed, img, skip_unread=True, fuse_q1="stream")
     torch.cuda.synchronize()
     assert ops.status() == 0
     assert torch.equal(raw_f["deltas"], raw_u["deltas"])
+    assert torch.equal(raw_s["deltas"], raw_u["deltas"])
     for k in ("logits", "logvar", "regvar"):
-        want, got = ops.sample_mean_q1(raw_u[k]), raw_f[k][:, 0]
-        assert float((got - want).abs().max()) <= 2e-6 * float(want.abs().max()), k
+        want = ops.sample_mean_q1(raw_u[k])
+        for got in (raw_f[k][:, 0], raw_s[k][:, 0]):
+            assert float((got - want).abs().max()) <= 2e-6 * float(want.abs().max()), k

@@ -8,7 +8,11 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GO, PR = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+GO = os.path.join(ROOT, "gpurun_out")
+# on the GPU box the summaries go to gpurun_out/<tag>_profiles (only gpurun_out/ travels back, <= 64 MiB: the .ncu-rep
+# files are summarised there and deleted); here they are then copied into the tracked profiles/
+PR = os.environ.get("POD_PROFILE_OUT", os.path.join(ROOT, "profiles"))
+os.makedirs(PR, exist_ok=True)
 KEYS = ["dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "gpu__time_duration.sum", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
@@ -79,6 +83,34 @@ def bench_workloads():
     return bench.WORKLOADS
 
 
+def ncu_table(tag, name, title_lines, keep=None):
+    """Generic per-kernel summary of an ncu --set full report (one block per captured launch)."""
+    rep = os.path.join(GO, "%s_%s.ncu-rep" % (tag, name))
+    if not os.path.exists(rep):
+        return None
+    hdr, units, rows = raw_rows(rep)
+    lines = list(title_lines)
+    for r in rows:
+        kn = r[hdr.index("Kernel Name")]
+        if keep and not any(k in kn for k in keep):
+            continue
+        lines.append("")
+        lines.append("%-80s %s" % ("Kernel Name", kn))
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                lines.append("%-80s %s %s" % (k, r[i], units[i]))
+        rd, wr, t = r[hdr.index("dram__bytes_read.sum")], r[hdr.index("dram__bytes_write.sum")], r[hdr.index("gpu__time_duration.sum")]
+        try:
+            b = to_bytes(rd, units[hdr.index("dram__bytes_read.sum")]) + to_bytes(wr, units[hdr.index("dram__bytes_write.sum")])
+            tu = units[hdr.index("gpu__time_duration.sum")]
+            sec = float(t) * {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}.get(tu, 1e-9)
+            lines.append("%-80s %.1f GB/s" % ("=> DRAM read+write / duration", b / sec / 1e9))
+        except Exception:  # noqa: BLE001
+            pass
+    return lines
+
+
 def main():
     tag = sys.argv[1]
     for f in ("bench_n1.json", "reference_arm.json", "clocks.csv"):
@@ -87,6 +119,11 @@ def main():
             dst = {"bench_n1.json": "%s_bench_n1_batch32.json", "reference_arm.json": "%s_bench_reference_arm.json",
                    "clocks.csv": "%s_clocks_during_bench.csv"}[f] % tag
             shutil.copy(src, os.path.join(PR, dst))
+    for f in ("sanitizer_memcheck.txt", "sanitizer_racecheck.txt", "sanitizer_synccheck.txt", "bayesod_envelope.txt", "mma_shape.txt",
+              "q1_experiments.txt", "tower_clock.txt", "pytest_gpu.txt"):
+        src = os.path.join(GO, "%s_%s" % (tag, f))
+        if os.path.exists(src):
+            shutil.copy(src, os.path.join(PR, "%s_%s" % (tag, f)))
     open(os.path.join(PR, "%s_launch_shares.txt" % tag), "w").write("\n".join(launches(tag)) + "\n")
     lines, res = ncu_summary(tag, "tower", [
         "# %s: ncu --set full --clock-control none -k regex:^k_conv3x3_tc2$ -s 1 -c 1  (bench.py --batch 2 --chunk 2)" % tag,
@@ -106,24 +143,33 @@ def main():
               open(os.path.join(PR, "conv_traffic.json"), "w"), indent=1)
     lines, _ = ncu_summary(tag, "out", [
         "# %s: ncu --set full --clock-control none -k regex:^k_conv3x3_wt$ -c 3  (bench.py --batch 2 --chunk 2)" % tag,
-        "# kernels: the output convolutions at P3 (cls_score 63, cls_var 63, bbox_pred 36 channels, all padded to 64 rows), single CTA,",
-        "# weights-as-A: stacked [w_hi; w_lo] as the M=128 operand, 16x16 pixels as N=256, 2 MMAs per K-step"])
+        "# kernels: the output convolutions at P3 (weights-as-A: stacked [w_hi; w_lo] as the M=128 operand, 16x16 pixels as N=256,",
+        "# 2 MMAs per K-step); with the fused sample mean cls_score / cls_var run on ONE mean map per image, bbox_pred per sample"])
     open(os.path.join(PR, "%s_out_conv_ncu_full.txt" % tag), "w").write("\n".join(lines) + "\n")
+    for name, fn, title in (
+            ("hbm", "hbm_kernels_ncu.txt", ["# %s: ncu --set full -k regex:^(k_q1_mean_act|k_mask_expand|k_sample_mean_q1_v4)$ -c 3 (bench.py --batch 4 --chunk 4)" % tag,
+                                            "# the HBM-bound streaming kernels of the step (first launches = P3, class tower)"]),
+            ("backbone", "backbone_ncu.txt", ["# %s: ncu --set full -k regex:^(k_conv3x3_tc|k_stem_conv7|k_maxpool3s2)$ -s 2 -c 8" % tag,
+                                              "# (bench.py --workload loss_att --from-images --batch 4): stem + first bottleneck convolutions of the ResNet-50-FPN backbone"]),
+            ("post", "post_kernels_ncu.txt", ["# %s: ncu --set full -k regex:^(k_decode|k_nms_fuse|k_cluster_merge|k_scores|k_topk)$ -c 10" % tag,
+                                              "# (bench.py --workload mc_post --n-mc 30 --batch 4): the post-processing kernels of the post-NMS merge mode (120 runs per launch)"])):
+        t = ncu_table(tag, name, title)
+        if t:
+            open(os.path.join(PR, "%s_%s" % (tag, fn)), "w").write("\n".join(t) + "\n")
     side = os.path.join(GO, "%s_side_workloads.jsonl" % tag)
     if os.path.exists(side):
-        out = ["# %s side workloads on ONE B200, batch 32 per step (python bench.py --workload <w> --no-cpu-baseline); not the headline metric" % tag,
-               "%-14s %9s %10s %9s %11s %9s %7s" % ("workload", "images/s", "e2e img/s", "mma_frac", "conv share", "launches", "SM MHz")]
+        out = ["# %s side workloads on ONE B200 (python bench.py --workload <w> ... --no-cpu-baseline); not the headline metric" % tag,
+               "%9s %10s %9s %9s %7s  %s" % ("images/s", "e2e img/s", "ms/step", "launches", "SM MHz", "workload")]
         for ln in open(side):
             ln = ln.strip()
             if not ln.startswith("{"):
                 continue
             j = json.loads(ln)
-            r = j.get("roofline") or {}
-            wl = j["config"]["workload"]
-            name = [k for k, v in bench_workloads().items() if wl.startswith(v[0])]
-            out.append("%-14s %9.1f %10.1f %9.3f %11.3f %9d %7s   # %s" % (name[0] if name else "?", j["value"], j["e2e"]["value"],
-                       r.get("mma_frac", float("nan")), r.get("conv_share_of_step", float("nan")), j["gpu_launches"],
-                       j["clocks"]["sm_mhz"], wl))
+            out.append("%9.1f %10.1f %9.2f %9d %7s  %s%s" % (j["value"], j["e2e"]["value"], j["ms_per_step"], j["gpu_launches"],
+                       j["clocks"]["sm_mhz"], j["config"]["workload"], " [CUDA graph]" if j["config"].get("cuda_graph") else ""))
+            by = (j.get("roofline") or {}).get("ms_per_step_by_kernel")
+            if by:
+                out.append("%49s per-step kernel ms: %s" % ("", by))
         open(os.path.join(PR, "%s_side_workloads.txt" % tag), "w").write("\n".join(out) + "\n")
     print("value", bj["value"], "e2e", bj["e2e"]["value"], "roofline", bj["roofline"]["frac"], bj["roofline"]["mma_frac"])
 
