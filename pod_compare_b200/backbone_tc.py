@@ -115,6 +115,13 @@ class TcResNetFPNBackbone:
 
     @torch.no_grad()
     def __call__(self, images):
+        torch.cuda.nvtx.range_push("pod.backbone")
+        try:
+            return self._forward(images)
+        finally:
+            torch.cuda.nvtx.range_pop()
+
+    def _forward(self, images):
         if isinstance(images, (list, tuple)):
             x = torch.stack([im.to(self.device) for im in images])
         else:

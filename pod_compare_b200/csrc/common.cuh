@@ -131,12 +131,15 @@ __device__ __forceinline__ void pod_box_muller(uint32_t wa, uint32_t wb, float& 
 }
 
 // fp16 split of x*scale: hi = rn(x*scale), lo = rn(x*scale - hi), with lo rounded to POD_LO_BITS mantissa bits.
-// hi carries 11 significant bits and lo continues them, so the pair holds 12 + POD_LO_BITS + 1 significant bits: 20 at
-// the default of 7 -- a representation error of 2^-21 (4.8e-7 max, 2.8e-7 rms per element), below the 1.4e-6 rms the
-// tensor core's truncating accumulation leaves in a convolution anyway.  Why not all 10 bits: the tower kernel is
-// power-bound and the multipliers' energy depends on the operand bits -- measured with
-// tools/tower_clock_probe.py at the 1 kW cap: 34.9 ms per P3 launch with 10 lo mantissa bits, 33.9 with 5, 32.6 with
-// 0, 30.8 with lo = 0 (profiles/r2b_lo_bits.txt).  Low-order bits that no tolerance can see were costing clock.
+// hi carries 11 significant bits (|x*s - hi| <= 2^-11 |x*s|) and lo continues them with POD_LO_BITS + 1 more, so the
+// pair represents x*s to 2^-(12 + POD_LO_BITS): 2^-19 = 1.9e-6 worst case, ~8e-7 rms per element at the default of 7
+// (2^-22 with all 10 bits) -- the size of the 1.4e-6 rms the tensor core's truncating accumulation leaves in a
+// convolution anyway; measured end to end at 1280x720 the scores / boxes / covariances deviate from the oracle by
+// 1.13e-5 / 1.3e-3 px / 4.9e-5 with 7 bits against 1.12e-5 / 1.4e-3 px / 5.3e-5 with 10 (profiles/r2b_lo_bits.txt).
+// Why not all 10 bits: the tower kernel is power-bound and the multipliers' energy depends on the
+// operand bits -- measured with tools/tower_clock_probe.py at the 1 kW cap: 34.9 ms per P3 launch with 10 lo mantissa
+// bits, 33.9 with 5, 32.6 with 0, 30.8 with lo = 0; whole step, same box: 615.8 ms (10 bits), 608.1 (7), 601.2 (5).
+// Low-order bits that no tolerance can see were costing clock.
 #ifndef POD_LO_BITS
 #define POD_LO_BITS 7
 #endif

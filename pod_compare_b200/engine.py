@@ -25,6 +25,21 @@ import torch
 from . import ops
 from ._cabi import POD_OUT_HIDDEN, POD_OUT_RAW, PodError
 
+class nvtx_range:
+    """NVTX range around a stage of the path (visible in nsys / ncu --nvtx timelines; a few hundred nanoseconds when no
+    profiler is attached)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        torch.cuda.nvtx.range_pop()
+        return False
+
+
 ACT_SCALE = 16.0          # largest fp16 split scale of activations (|x| < 4094, abs. resolution 2^-28); the scale of a call is
                           # min(ACT_SCALE, largest power of two s with max|feature| * s <= FEATURE_TARGET), a device word
 FEATURE_TARGET = 128.0    # = 8 * ACT_SCALE: stored features stay below 128, leaving 512x headroom (65504 / 128) for hidden
@@ -211,7 +226,7 @@ class HeadEngine:
         tower and the variance pass of the box tower of sample N-1: 9 of the 12N+2 tower convolutions and 3 of
         the 4N output convolutions); rows [:, N-1] of logits / logvar / regvar are then left unwritten.  Valid
         only when the caller aggregates with the Q1 mean (pre-NMS modes), never for per-run inference."""
-        pc, w = self.pc, self.ws[0]
+        pc = self.pc
         B = feats[0].shape[0]
         A, K = pc.num_anchors, pc.num_classes
         level_hw = [tuple(f.shape[-2:]) for f in feats]
@@ -231,94 +246,107 @@ class HeadEngine:
                "logvar": torch.empty((B, n_stat, R, K), dtype=torch.float32, device=dev) if pc.cls_var else None,
                "regvar": torch.empty((B, n_stat, R, pc.cov_dims), dtype=torch.float32, device=dev) if pc.bbox_cov else None}
         max_hw = max(h * wd for h, wd in level_hw)
-        groups = (n_mc + Q1_GROUP - 1) // Q1_GROUP
+        nmaps = B * n_mc * passes
+        st = {"n_mc": n_mc, "seed": seed, "image0": image0, "skip_unread": skip_unread, "fuse": fuse, "in_epilogue": in_epilogue,
+              "raw": raw, "level_off": level_off, "R": R, "B": B,
+              "act": [(self._get("a%d_hi" % i, nmaps * max_hw * 256, torch.float16),
+                       self._get("a%d_lo" % i, nmaps * max_hw * 256, torch.float16)) for i in range(2)],
+              "c1": self._get("c1", B * max_hw * 256, torch.float32),
+              "groups": (n_mc + Q1_GROUP - 1) // Q1_GROUP, "q1_acc": None, "q1_mean": None}
         if fuse:
             if in_epilogue:
-                q1_acc = self._get("q1_acc", B * 2 * groups * max_hw * 256, torch.float32)
-            q1_mean = (self._get("q1m_hi", B * 2 * max_hw * 256, torch.float16), self._get("q1m_lo", B * 2 * max_hw * 256, torch.float16))
-        nmaps = B * n_mc * passes
-        act = [(self._get("a%d_hi" % i, nmaps * max_hw * 256, torch.float16),
-                self._get("a%d_lo" % i, nmaps * max_hw * 256, torch.float16)) for i in range(2)]
-        c1 = self._get("c1", B * max_hw * 256, torch.float32)
+                st["q1_acc"] = self._get("q1_acc", B * 2 * st["groups"] * max_hw * 256, torch.float32)
+            st["q1_mean"] = (self._get("q1m_hi", B * 2 * max_hw * 256, torch.float16),
+                             self._get("q1m_lo", B * 2 * max_hw * 256, torch.float16))
         fscale = self.feature_scale(feats)
         for lvl, f in enumerate(feats):
             H, W = level_hw[lvl]
-            HW = H * W
             fhi, flo = self._split_input(f, fscale)
             for tower in (TOWER_CLS, TOWER_BOX):
-                tw = w.towers[tower]
-                has_var = pc.cls_var if tower == TOWER_CLS else pc.bbox_cov
-                t_passes = 2 if has_var else 1
-                # layer 0: conv + ReLU once per image, then N x passes masked copies (Q2 hoist)
-                p0 = tw[0]
-                ops.conv3x3_tc(fhi, flo, 1.0, B, H, W, 256, p0.w_hi, p0.w_lo, p0.w_scale, p0.bias, 256, 256,
-                               POD_OUT_RAW, True, out_f32=c1, out_map_stride=HW * 256, out_pixel_stride=256,
-                               in_scale_dev=fscale)
-                d0 = ops.make_dropout(pc.dropout_rate, seed, image0, n_mc, t_passes, 0, tower, 0, lvl)
-                # maps of one image: sample-major, pass-minor; the unread ones (skip_unread) are its tail
-                grp = n_mc * t_passes
-                live = grp
-                if skip_unread and n_mc > 1:
-                    live = (n_mc - 1) * t_passes + (0 if tower == TOWER_CLS else 1)
-                ops.mask_expand_split(c1[: B * HW * 256].view(B, HW, 256), d0, 1.0, act[0][0], act[0][1], live_reps=live,
-                                      scale_dev=fscale)
-                cur = 0
-                NB = B * n_mc * t_passes
-                # passes of this tower whose last layer is only ever averaged over the samples (fused Q1 accumulation)
-                acc_mask = 0
-                if fuse:
-                    acc_mask = ((1 << t_passes) - 1) if tower == TOWER_CLS else (2 if has_var else 0)
-                n_acc = bin(acc_mask).count("1")
-                for layer in range(1, len(tw)):
-                    d = ops.make_dropout(pc.dropout_rate, seed, image0, n_mc, t_passes, 0, tower, layer, lvl)
-                    q1_live = [n_mc - 1, n_mc - 1] if tower == TOWER_CLS else [n_mc, n_mc - 1]
-                    if acc_mask and layer == len(tw) - 1 and in_epilogue:
-                        ops.conv3x3_tc(act[cur][0], act[cur][1], 1.0, NB, H, W, 256, tw[layer].w_hi, tw[layer].w_lo,
-                                       tw[layer].w_scale, tw[layer].bias, 256, 256, POD_OUT_HIDDEN, True,
-                                       out_hi=act[cur ^ 1][0], out_lo=act[cur ^ 1][1], out_scale=1.0, drop=d,
-                                       in_scale_dev=fscale, out_scale_dev=fscale,
-                                       q1={"acc": q1_acc, "samples": n_mc, "passes": t_passes, "live": q1_live[:t_passes],
-                                           "mask": acc_mask, "group": Q1_GROUP})
-                        ops.q1_finish(q1_acc, B * n_acc, groups, HW * 256, n_mc, fscale, q1_mean[0], q1_mean[1])
-                    else:
-                        self._conv_hidden(act[cur], NB, H, W, tw[layer], act[cur ^ 1], d, fscale, map_group=grp, map_live=live,
-                                          tag="tower256" if not self.profile_layers else "tower256_L%d" % layer)
-                        if acc_mask and layer == len(tw) - 1:
-                            # streaming form (default): the per-sample maps just written are averaged by one HBM-bound pass
-                            ops.q1_mean_act(act[cur ^ 1][0], act[cur ^ 1][1], B, n_mc, t_passes, acc_mask, q1_live[:t_passes],
-                                            HW * 256, fscale, q1_mean[0], q1_mean[1])
-                    cur ^= 1
-                n_live = n_mc - 1 if (skip_unread and n_mc > 1) else n_mc        # samples whose mean/var heads are read
-                # output convs: pass-0 maps feed the mean head, pass-1 maps the variance head (Q2)
-                mean_pc, var_pc = (w.cls_score, w.cls_var) if tower == TOWER_CLS else (w.bbox_pred, w.bbox_cov)
-                mean_out = raw["logits"] if tower == TOWER_CLS else raw["deltas"]
-                D = mean_pc[0].total_cout // A
-                if acc_mask:
-                    # the averaged outputs: ONE convolution per image on the mean activation (accumulated pass a of image b
-                    # is map b * n_acc + a of q1_mean)
-                    a_idx = 0
-                    if tower == TOWER_CLS:
-                        self._conv_out(q1_mean, B, H, W, mean_pc, mean_out, level_off[lvl] * D, R * D, fscale,
-                                       in_map_stride=n_acc * HW * 256, in_offset=0)
-                        a_idx = 1
-                    else:
-                        self._conv_out(act[cur], B * n_mc, H, W, mean_pc, mean_out, level_off[lvl] * D, R * D, fscale,
-                                       in_map_stride=t_passes * HW * 256, in_offset=0, map_group=n_mc, map_live=n_mc)
-                    if has_var:
-                        var_out = raw["logvar"] if tower == TOWER_CLS else raw["regvar"]
-                        Dv = var_pc[0].total_cout // A
-                        self._conv_out(q1_mean, B, H, W, var_pc, var_out, level_off[lvl] * Dv, R * Dv, fscale,
-                                       in_map_stride=n_acc * HW * 256, in_offset=a_idx * HW * 256)
-                    continue
-                self._conv_out(act[cur], B * n_mc, H, W, mean_pc, mean_out, level_off[lvl] * D, R * D, fscale,
-                               in_map_stride=t_passes * HW * 256, in_offset=0, map_group=n_mc,
-                               map_live=n_live if tower == TOWER_CLS else n_mc)
-                if has_var:
-                    var_out = raw["logvar"] if tower == TOWER_CLS else raw["regvar"]
-                    Dv = var_pc[0].total_cout // A
-                    self._conv_out(act[cur], B * n_mc, H, W, var_pc, var_out, level_off[lvl] * Dv, R * Dv, fscale,
-                                   in_map_stride=2 * HW * 256, in_offset=HW * 256, map_group=n_mc, map_live=n_live)
+                with nvtx_range("pod.head_mc.P%d.%s" % (lvl + 3, "cls" if tower == TOWER_CLS else "box")):
+                    self._head_mc_tower(st, lvl, tower, H, W, fhi, flo, fscale)
         return raw, level_off
+
+    def _head_mc_tower(self, st, lvl, tower, H, W, fhi, flo, fscale):
+        """One (level, tower) unit of head_mc: hoisted first layer, mask replication, masked tower layers, output heads."""
+        pc, w = self.pc, self.ws[0]
+        n_mc, seed, image0, B, R = st["n_mc"], st["seed"], st["image0"], st["B"], st["R"]
+        skip_unread, fuse, in_epilogue = st["skip_unread"], st["fuse"], st["in_epilogue"]
+        act, c1, raw, level_off, groups, q1_acc, q1_mean = (st[k] for k in ("act", "c1", "raw", "level_off", "groups", "q1_acc", "q1_mean"))
+        A = pc.num_anchors
+        HW = H * W
+        tw = w.towers[tower]
+        has_var = pc.cls_var if tower == TOWER_CLS else pc.bbox_cov
+        t_passes = 2 if has_var else 1
+        # layer 0: conv + ReLU once per image, then N x passes masked copies (Q2 hoist)
+        p0 = tw[0]
+        ops.conv3x3_tc(fhi, flo, 1.0, B, H, W, 256, p0.w_hi, p0.w_lo, p0.w_scale, p0.bias, 256, 256,
+                       POD_OUT_RAW, True, out_f32=c1, out_map_stride=HW * 256, out_pixel_stride=256,
+                       in_scale_dev=fscale)
+        d0 = ops.make_dropout(pc.dropout_rate, seed, image0, n_mc, t_passes, 0, tower, 0, lvl)
+        # maps of one image: sample-major, pass-minor; the unread ones (skip_unread) are its tail
+        grp = n_mc * t_passes
+        live = grp
+        if skip_unread and n_mc > 1:
+            live = (n_mc - 1) * t_passes + (0 if tower == TOWER_CLS else 1)
+        ops.mask_expand_split(c1[: B * HW * 256].view(B, HW, 256), d0, 1.0, act[0][0], act[0][1], live_reps=live,
+                              scale_dev=fscale)
+        cur = 0
+        NB = B * n_mc * t_passes
+        # passes of this tower whose last layer is only ever averaged over the samples (fused Q1 mean)
+        acc_mask = 0
+        if fuse:
+            acc_mask = ((1 << t_passes) - 1) if tower == TOWER_CLS else (2 if has_var else 0)
+        n_acc = bin(acc_mask).count("1")
+        q1_live = [n_mc - 1, n_mc - 1] if tower == TOWER_CLS else [n_mc, n_mc - 1]
+        for layer in range(1, len(tw)):
+            d = ops.make_dropout(pc.dropout_rate, seed, image0, n_mc, t_passes, 0, tower, layer, lvl)
+            if acc_mask and layer == len(tw) - 1 and in_epilogue:
+                ops.conv3x3_tc(act[cur][0], act[cur][1], 1.0, NB, H, W, 256, tw[layer].w_hi, tw[layer].w_lo,
+                               tw[layer].w_scale, tw[layer].bias, 256, 256, POD_OUT_HIDDEN, True,
+                               out_hi=act[cur ^ 1][0], out_lo=act[cur ^ 1][1], out_scale=1.0, drop=d,
+                               in_scale_dev=fscale, out_scale_dev=fscale,
+                               q1={"acc": q1_acc, "samples": n_mc, "passes": t_passes, "live": q1_live[:t_passes],
+                                   "mask": acc_mask, "group": Q1_GROUP})
+                ops.q1_finish(q1_acc, B * n_acc, groups, HW * 256, n_mc, fscale, q1_mean[0], q1_mean[1])
+            else:
+                self._conv_hidden(act[cur], NB, H, W, tw[layer], act[cur ^ 1], d, fscale, map_group=grp, map_live=live,
+                                  tag="tower256" if not self.profile_layers else "tower256_L%d" % layer)
+                if acc_mask and layer == len(tw) - 1:
+                    # streaming form (default): the per-sample maps just written are averaged by one HBM-bound pass
+                    ops.q1_mean_act(act[cur ^ 1][0], act[cur ^ 1][1], B, n_mc, t_passes, acc_mask, q1_live[:t_passes],
+                                    HW * 256, fscale, q1_mean[0], q1_mean[1])
+            cur ^= 1
+        n_live = n_mc - 1 if (skip_unread and n_mc > 1) else n_mc        # samples whose mean/var heads are read
+        # output convs: pass-0 maps feed the mean head, pass-1 maps the variance head (Q2)
+        mean_pc, var_pc = (w.cls_score, w.cls_var) if tower == TOWER_CLS else (w.bbox_pred, w.bbox_cov)
+        mean_out = raw["logits"] if tower == TOWER_CLS else raw["deltas"]
+        D = mean_pc[0].total_cout // A
+        if acc_mask:
+            # the averaged outputs: ONE convolution per image on the mean activation (accumulated pass a of image b
+            # is map b * n_acc + a of q1_mean)
+            a_idx = 0
+            if tower == TOWER_CLS:
+                self._conv_out(q1_mean, B, H, W, mean_pc, mean_out, level_off[lvl] * D, R * D, fscale,
+                               in_map_stride=n_acc * HW * 256, in_offset=0)
+                a_idx = 1
+            else:
+                self._conv_out(act[cur], B * n_mc, H, W, mean_pc, mean_out, level_off[lvl] * D, R * D, fscale,
+                               in_map_stride=t_passes * HW * 256, in_offset=0, map_group=n_mc, map_live=n_mc)
+            if has_var:
+                var_out = raw["logvar"] if tower == TOWER_CLS else raw["regvar"]
+                Dv = var_pc[0].total_cout // A
+                self._conv_out(q1_mean, B, H, W, var_pc, var_out, level_off[lvl] * Dv, R * Dv, fscale,
+                               in_map_stride=n_acc * HW * 256, in_offset=a_idx * HW * 256)
+            return
+        self._conv_out(act[cur], B * n_mc, H, W, mean_pc, mean_out, level_off[lvl] * D, R * D, fscale,
+                       in_map_stride=t_passes * HW * 256, in_offset=0, map_group=n_mc,
+                       map_live=n_live if tower == TOWER_CLS else n_mc)
+        if has_var:
+            var_out = raw["logvar"] if tower == TOWER_CLS else raw["regvar"]
+            Dv = var_pc[0].total_cout // A
+            self._conv_out(act[cur], B * n_mc, H, W, var_pc, var_out, level_off[lvl] * Dv, R * Dv, fscale,
+                           in_map_stride=2 * HW * 256, in_offset=HW * 256, map_group=n_mc, map_live=n_live)
 
     def head_eval(self, feats, members=None, skip_unread=False, per_member_feats=False):
         """Deterministic head (eval mode): one forward per weight set; the reference's second tower
@@ -364,6 +392,7 @@ class HeadEngine:
                 for tower in (TOWER_CLS, TOWER_BOX):
                     if skip_unread and E > 1 and e == E - 1 and tower == TOWER_CLS:
                         continue
+                    torch.cuda.nvtx.range_push("pod.head_eval.P%d.m%d.%s" % (lvl + 3, e, "cls" if tower == TOWER_CLS else "box"))
                     tw = w.towers[tower]
                     src, cur = (fhi, flo), 0
                     for layer in range(len(tw)):
@@ -385,12 +414,14 @@ class HeadEngine:
                                            out_map_stride=E * R * D, out_pixel_stride=A * D,
                                            out2_f32=var_out, out2_offset=(e * R + level_off[lvl]) * Dv,
                                            split_col=split - pcv.col0, out2_map_stride=E * R * Dv, out2_pixel_stride=A * Dv)
+                        torch.cuda.nvtx.range_pop()
                         continue
                     self._conv_out(src, B, H, W, mean_pc, mean_out, (e * R + level_off[lvl]) * D, E * R * D, fscale)
                     if var_pc is not None:
                         var_out = raw["logvar"] if tower == TOWER_CLS else raw["regvar"]
                         Dv = var_pc[0].total_cout // A
                         self._conv_out(src, B, H, W, var_pc, var_out, (e * R + level_off[lvl]) * Dv, E * R * Dv, fscale)
+                    torch.cuda.nvtx.range_pop()
         return raw, level_off
 
     # ------------------------------------------------------------------ statistics + post-processing
@@ -416,20 +447,23 @@ class HeadEngine:
                 m_logits, m_deltas = m_logits.contiguous(), m_deltas.contiguous()
                 m_logvar = m_logvar.contiguous() if m_logvar is not None else None
                 m_regvar = m_regvar.contiguous() if m_regvar is not None else None
-        probs, score, cls = ops.scores(m_logits, m_logvar, level_off, pc.cls_var_num_samples, seed, image0, runs=runs)
-        cand_idx, cand_cnt, seg = ops.topk_levels(score, level_off, pc.topk, pc.score_thresh)
-        cand = ops.decode_cov(m_deltas, m_regvar, raw["deltas"] if S > 1 else None, anchors, probs, score, cls,
-                              cand_idx, cand_cnt, seg, pc.box_num_samples, seed, image0, pc.reg_weights, runs=runs,
-                              sample_reg_weights=pc.sample_reg_weights)
+        with nvtx_range("pod.scores_topk"):
+            probs, score, cls = ops.scores(m_logits, m_logvar, level_off, pc.cls_var_num_samples, seed, image0, runs=runs)
+            cand_idx, cand_cnt, seg = ops.topk_levels(score, level_off, pc.topk, pc.score_thresh)
+        with nvtx_range("pod.decode_cov"):
+            cand = ops.decode_cov(m_deltas, m_regvar, raw["deltas"] if S > 1 else None, anchors, probs, score, cls,
+                                  cand_idx, cand_cnt, seg, pc.box_num_samples, seed, image0, pc.reg_weights, runs=runs,
+                                  sample_reg_weights=pc.sample_reg_weights)
         return cand
 
     def detections(self, cand, fuse_mode, image_hw, out_hw, nms_variant=ops.NMS_AUTO, skip_post=False):
         """fuse_mode: 0 standard NMS, 1 BayesOD, 2 anchor statistics."""
         pc = self.pc
-        return ops.nms_fuse(cand, int(fuse_mode), pc.nms_thresh, pc.affinity, pc.max_dets, image_hw, out_hw,
-                            nms_variant=nms_variant, skip_post=skip_post,
-                            box_merge=0 if pc.box_merge == "bayesian_inference" else 1,
-                            cls_merge=0 if pc.cls_merge == "max_score" else 1)
+        with nvtx_range("pod.nms_fuse"):
+            return ops.nms_fuse(cand, int(fuse_mode), pc.nms_thresh, pc.affinity, pc.max_dets, image_hw, out_hw,
+                                nms_variant=nms_variant, skip_post=skip_post,
+                                box_merge=0 if pc.box_merge == "bayesian_inference" else 1,
+                                cls_merge=0 if pc.cls_merge == "max_score" else 1)
 
 
     def merged_detections(self, raw, level_off, anchors, seed, image0, image_hw, out_hw):

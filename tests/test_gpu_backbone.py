@@ -86,7 +86,7 @@ def test_stem_pool_upsample_and_split_kernels():
         ops.stem_conv7_pool(im.contiguous(), H, W, mean, std, w.permute(2, 3, 1, 0).reshape(147, 64).contiguous().cuda(), b.cuda(), scratch,
                             ohi, olo, TC.ACT)
         got = ((ohi.float() + olo.float()) / TC.ACT).permute(0, 3, 1, 2).cpu()
-        assert _rel(got, ref) <= 2e-6
+        assert _rel(got, ref) <= 4e-6            # fp32 SIMT convolution + the 2^-19 split of its output
     d = torch.randn((2, 5, 7, 16), generator=g).cuda()
     s = torch.randn((2, 3, 4, 16), generator=g).cuda()
     want = d + F.interpolate(s.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")[:, :, :5, :7].permute(0, 2, 3, 1)
@@ -94,7 +94,7 @@ def test_stem_pool_upsample_and_split_kernels():
     assert torch.equal(d, want)
     v = torch.randn((3, 4, 5, 8), generator=g).cuda() * 100
     hi, lo = ops.split_f32(v, scale=2.0, relu=True)
-    assert torch.allclose((hi.float() + lo.float()) / 2.0, torch.relu(v), rtol=6e-7, atol=1e-9)      # 20 significant bits
+    assert torch.allclose((hi.float() + lo.float()) / 2.0, torch.relu(v), rtol=2e-6, atol=1e-9)      # the pair holds x to 2^-19 (common.cuh POD_LO_BITS)
 
 
 @pytest.mark.parametrize("hw", [(100, 190), (720, 1280)])

@@ -306,7 +306,7 @@ def _align_by_id(ids_got, ids_ref, scores_ref, boundary_scores, group_of=None):
     return ig, ir
 
 
-def _compare_path(res, cand, det, ref_final, ref_cand, ref_det, pp, bayes, prob_atol=1e-7, prob_rtol=1e-4):
+def _compare_path(res, cand, det, ref_final, ref_cand, ref_det, pp, bayes, prob_atol=1e-7, prob_rtol=1e-4, box_atol=2e-3):
     M = int(cand["count"][0])
     ids_got = cand["anchor"][0, :M].cpu().numpy()
     sizes = np.cumsum([0] + [int(x.shape[0]) for x in ref_cand.level_scores])
@@ -326,7 +326,7 @@ def _compare_path(res, cand, det, ref_final, ref_cand, ref_det, pp, bayes, prob_
     assert np.array_equal(g("classes").astype(np.int64), ref_cand.classes.numpy()[ir])
     assert _close(g("scores"), ref_cand.scores.numpy()[ir], prob_rtol, prob_atol, "candidate scores")
     assert _close(g("probs"), ref_cand.probs.numpy()[ir], prob_rtol, prob_atol, "candidate probability vectors")
-    assert _close(g("boxes"), ref_cand.boxes.numpy()[ir], 1e-4, 2e-3, "candidate boxes")
+    assert _close(g("boxes"), ref_cand.boxes.numpy()[ir], 1e-4, box_atol, "candidate boxes")
     if isinstance(ref_cand.cov, torch.Tensor):
         assert _cov_close(g("cov"), ref_cand.cov.numpy()[ir], 2e-4)
     # detections: identified by the anchor id of the NMS survivor they come from
@@ -349,7 +349,7 @@ def _compare_path(res, cand, det, ref_final, ref_cand, ref_det, pp, bayes, prob_
     assert _close(res.pred_cls_probs.cpu().numpy()[i_g], ref_final.probs.numpy()[i_r], prob_rtol, prob_atol, "probability vectors")
     # BayesOD end to end: measured worst case 7.8e-4 px / 1.4e-5 at cond(sum P) = 4e2 (profiles/r2a_bayesod_envelope.txt);
     # the fused covariance is bounded at the north-star's 1e-4 (scaled by the matrix' largest entry), boxes at 3e-3 px
-    assert _close(res.pred_boxes.tensor.cpu().numpy()[i_g], ref_final.boxes.numpy()[i_r], 1e-4, 3e-3 if bayes else 2e-3, "boxes")
+    assert _close(res.pred_boxes.tensor.cpu().numpy()[i_g], ref_final.boxes.numpy()[i_r], 1e-4, max(box_atol, 3e-3) if bayes else box_atol, "boxes")
     assert _cov_close(res.pred_boxes_covariance.cpu().numpy()[i_g], ref_final.cov.numpy()[i_r], 1e-4 if bayes else 2e-4)
     # output order: descending score up to near-ties
     sc = res.scores.cpu().numpy()
@@ -602,7 +602,9 @@ def test_predictor_from_raw_images_with_backbone():
     # moves by dp/p = (1 - p) * d(logit): the head's ~1e-5 relative accuracy of the largest logit is an
     # ABSOLUTE logit error of up to ~4e-4 here, i.e. up to 4e-4 relative on a probability -- the same conditioning limits
     # any fp32 evaluation, the reference's included.  Measured worst case 2.0e-4 (r2f); bound 5e-4, floor 2e-6.
-    _compare_path(ref[0], cand, det, ref_final, ref_cand, ref_det, pp, False, prob_atol=2e-6, prob_rtol=5e-4)
+    # The regression deltas are ~15x larger too (boxes move by hundreds of pixels, many clamp at exp(4.135)): the same
+    # relative accuracy is 1e-2 px here instead of 2e-3 (measured worst case 2.8e-3, r2j).
+    _compare_path(ref[0], cand, det, ref_final, ref_cand, ref_det, pp, False, prob_atol=2e-6, prob_rtol=5e-4, box_atol=1e-2)
 
 
 def test_large_feature_magnitudes_are_rescaled():
