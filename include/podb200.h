@@ -171,6 +171,16 @@ typedef struct pod_conv_args {
   int q1_live[2];
   int q1_acc_mask;
   int q1_group;
+  /* Optional in-kernel dropout of the INPUT (first masked tower layer; POD_OUT_HIDDEN, 256 -> 256, CTA-pair kernel):
+   * with mask_in = 1 the input holds ONE map per image -- the mask-independent first tower layer, already multiplied by
+   * 1/(1-p) (produced by a launch with drop_scale_only = 1) -- and output map n = (image, sample, pass) reads it with
+   * the keep mask of stream layer mask_in_layer applied to the staged tile in shared memory.  Replaces
+   * pod_mask_expand_split + a plain launch bit for bit; the samples x passes masked copies never exist in HBM
+   * (probabilistic_retinanet.py:422-424 applied 16N times per level in the reference). */
+  int mask_in;
+  int mask_in_layer;
+  /* POD_OUT_HIDDEN with drop.p > 0: multiply by 1/(1-p) and keep every element (no mask). */
+  int drop_scale_only;
 } pod_conv_args;
 int pod_conv3x3_tc(const pod_conv_args* a, void* stream);
 /* Channels per pipeline stage of the tcgen05 kernel: 64 (SWIZZLE_128B operand tiles, default) or

@@ -44,7 +44,8 @@ class ConvArgs(C.Structure):
                 ("out2_pixel_stride", C.c_int64), ("map_group", C.c_int), ("map_live", C.c_int),
                 ("in_scale_dev", C.c_void_p), ("out_scale_dev", C.c_void_p),
                 ("q1_acc", C.c_void_p), ("q1_samples", C.c_int), ("q1_passes", C.c_int), ("q1_live", C.c_int * 2),
-                ("q1_acc_mask", C.c_int), ("q1_group", C.c_int)]
+                ("q1_acc_mask", C.c_int), ("q1_group", C.c_int), ("mask_in", C.c_int), ("mask_in_layer", C.c_int),
+                ("drop_scale_only", C.c_int)]
 
 
 class DecodeArgs(C.Structure):

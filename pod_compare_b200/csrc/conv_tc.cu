@@ -28,6 +28,7 @@
 #include <cuda.h>
 #include <cstring>
 #include <cstdlib>
+#include <type_traits>
 
 namespace tc {
 
@@ -82,6 +83,12 @@ struct Params {
   const __half* res_hi;       // optional residual (split pair, layout of the HIDDEN output) added before the ReLU
   const __half* res_lo;
   float res_inv_scale;
+  // Input masking (CTA-pair kernel, FIRST masked tower layer; template MASKA): the A operand is the mask-independent
+  // first-layer activation c1 (one map per IMAGE, already multiplied by 1/(1-p)); the dropout mask of (sample, pass) is
+  // applied to the staged tile in shared memory by warps 2-3, so the N x passes masked copies never exist in HBM.
+  int mask_in;                // 1: MASKA launch
+  int mask_in_layer;          // layer index of the mask stream applied to the input (0)
+  int drop_scale_only;        // HIDDEN epilogue: multiply by 1/(1-p) but keep every element (producer of c1)
   // Q1 sample accumulation (CTA-pair kernel, last tower layer): see TileRef / tile_ref2 below
   int q1_mode;          // 0 = plain tile order
   int q1_samples;       // S: MC samples per image; maps of an image are ordered sample-major, pass-minor
@@ -458,6 +465,9 @@ __device__ __forceinline__ void tile_epilogue(const Params& P, const float (&sum
           const uint32_t bits = keep[g / 2] >> ((g % 2) * 16);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = ((bits >> i) & 1u) ? v[i] * P.drop_scale : 0.f;
+        } else if (P.drop_scale_only) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= P.drop_scale;
         }
         // the fp16 split pair holds |x * out_scale| <= 65504; beyond it hi becomes inf and every later layer NaN.
         // The reference computes in fp32 and has no such limit, so this is reported, never silent (also catches NaN).
@@ -823,6 +833,11 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_smem_addr, uint3
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// same, releasing this CTA's prior writes at cluster scope (the waiter may sit in the other CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tma2_load_4d(const CUtensorMap* tm, uint32_t mbar_cluster_addr, void* dst, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -861,6 +876,18 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint32_t leader) 
       ::"r"(smem_u32(bar)), "h"((uint16_t)3), "r"(leader) : "memory");
 }
 
+// MASKA: a third activation stage hides the extra hop (TMA -> mask warps -> MMA) of the in-kernel input masking
+struct CfgH2M {
+  static constexpr int B_HALF = 128 * 128;
+  static constexpr int B_STAGE = 2 * B_HALF;
+  static constexpr int A_STAGES = 3;
+  static constexpr int B_STAGES = (HALO_SMEM_BUDGET - 1024 - A_STAGES * HALO_A_STAGE) / B_STAGE;
+  static constexpr int SMEM_BYTES = 1024 + A_STAGES * HALO_A_STAGE + B_STAGES * B_STAGE;
+  static_assert(B_STAGES >= 3, "weight ring too shallow");
+};
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 template <int BK>
 struct Cfg2 {
   static constexpr int ROW_BYTES = BK * 2;
@@ -874,11 +901,12 @@ struct Cfg2 {
   static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 };
 
-template <int BK, int MODE, bool HALO>
+template <int BK, int MODE, bool HALO, bool MASKA = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc2(const __grid_constant__ Params P) {
   using C = Cfg2<BK>;
-  using CH = CfgH2;                                     // each CTA stages 128 of the 256 weight rows
+  using CH = typename std::conditional<MASKA, CfgH2M, CfgH2>::type;   // each CTA stages 128 of the 256 weight rows
   static_assert(!HALO || BK == 64, "row-halo staging needs 128-byte operand rows");
+  static_assert(!MASKA || (HALO && MODE == POD_OUT_HIDDEN), "input masking exists for the row-halo hidden-layer kernel");
   constexpr int STAGES = HALO ? CH::B_STAGES : C::STAGES;   // HALO: full/empty_bar track the WEIGHT ring
   constexpr int COLS = 128, NG = 8, EPI_THREADS = 256;
   extern __shared__ uint8_t smem_dyn[];
@@ -888,6 +916,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
   __shared__ __align__(8) uint64_t aempty_bar[HALO_A_STAGES_MAX];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];       // used in the leader CTA only
+  __shared__ __align__(8) uint64_t amask_bar[HALO_A_STAGES_MAX];   // MASKA: stage masked in BOTH CTAs (leader only)
+  __shared__ uint8_t s_keep[MASKA ? 2 * 5 * (TILE_W + 2) * 8 : 8];  // MASKA: keep bits of a K-block's halo region, per mask warp
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -914,6 +944,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 2 * EPI_THREADS / 32);  // one arrival per epilogue warp of BOTH CTAs
     }
+    for (int i = 0; i < HALO_A_STAGES_MAX; ++i) mbar_init(&amask_bar[i], 4);   // two mask warps in each CTA of the pair
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc2(&tmem_base_s, 512);
@@ -938,7 +969,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
   }
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  // warpgroup 0 keeps 40 registers (producer, MMA issuer) -- or 56 when its warps 2-3 run the input-mask loops with four
+  // Philox chains / four 16-byte chunks in flight.  56 is the ceiling: the kernel launches with 168 registers per thread,
+  // the epilogue warps' setmaxnreg.inc to 224 needs (224 - 168) x 256 = 14336 registers from the CTA's pool, and the pool
+  // only holds what warpgroup 0 released: (168 - 56) x 128 = 14336.  (64 leaves the pool 1024 short and the inc waits
+  // forever -- an unbounded hang, found the hard way.)
+  if constexpr (MASKA) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0 && lane == 0) {
     // ================================ TMA producer (both CTAs) ================================
     uint32_t stage = 0, phase = 0;
@@ -955,11 +992,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
         for (int cb = 0; cb < kb_per_tap && ok; ++cb) {
           for (int dx = 0; dx < 3 && ok; ++dx) {
             if (!mbar_wait(&aempty_bar[as], aphase ^ 1u, 15)) { ok = false; break; }
-            if (rank == 0) mbar_arrive_expect_tx(&afull_bar[as], 2u * (uint32_t)HALO_A_STAGE);
-            const uint32_t fa = mapa_cluster(smem_u32(&afull_bar[as]), 0);    // the leader's barriers
             uint8_t* sa = smem + (size_t)as * HALO_A_STAGE;
-            tma2_load_4d(&P.tm_a_hi, fa, sa, cb * 64, x0 + dx - 1, y0 - 1, n);
-            tma2_load_4d(&P.tm_a_lo, fa, sa + HALO_A_HALF, cb * 64, x0 + dx - 1, y0 - 1, n);
+            if constexpr (MASKA) {
+              // the tile of c1 (one map per image) lands under THIS CTA's barrier; its mask warps take it from there
+              const int reps = P.drop.samples * P.drop.passes;
+              const int img = tr.ok ? n / reps : P.NB / reps;           // no work: map index past the end -> zero fill
+              mbar_arrive_expect_tx(&afull_bar[as], (uint32_t)HALO_A_STAGE);
+              tma_load_4d(&P.tm_a_hi, &afull_bar[as], sa, cb * 64, x0 + dx - 1, y0 - 1, img);
+              tma_load_4d(&P.tm_a_lo, &afull_bar[as], sa + HALO_A_HALF, cb * 64, x0 + dx - 1, y0 - 1, img);
+            } else {
+              if (rank == 0) mbar_arrive_expect_tx(&afull_bar[as], 2u * (uint32_t)HALO_A_STAGE);
+              const uint32_t fa = mapa_cluster(smem_u32(&afull_bar[as]), 0);    // the leader's barriers
+              tma2_load_4d(&P.tm_a_hi, fa, sa, cb * 64, x0 + dx - 1, y0 - 1, n);
+              tma2_load_4d(&P.tm_a_lo, fa, sa + HALO_A_HALF, cb * 64, x0 + dx - 1, y0 - 1, n);
+            }
             if (++as == CH::A_STAGES) { as = 0; aphase ^= 1u; }
             for (int dy = 0; dy < 3; ++dy) {
               if (!mbar_wait(&empty_bar[stage], phase ^ 1u, 11)) { ok = false; break; }
@@ -990,6 +1036,104 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
       }
      }
     }
+  } else if (MASKA && (warp == 2 || warp == 3)) {
+    // ================================ input-mask warps (both CTAs) =============================
+    // Warp 2 owns rows 0-4 of every staged 10-row box, warp 3 rows 5-9.  Per K-block: the keep bits of the halo region
+    // (own 5 rows x 18 columns x 8 channel octets; one Philox call each) go into a small table while the TMA is in
+    // flight; per column shift dx: wait for the box, zero the dropped fp16 elements of its hi and lo halves in place
+    // (the kept ones already carry the 1/(1-p) factor), make the generic-proxy stores visible to the tensor core's
+    // async proxy, and tell the leader's MMA warp.
+    if constexpr (MASKA) {
+      uint32_t as = 0, aphase = 0;
+      bool ok = true;
+      const int row0 = (warp - 2) * 5;
+      uint8_t* tab = s_keep + (warp - 2) * (5 * (TILE_W + 2) * 8);
+      const int reps = P.drop.samples * P.drop.passes;
+      for (int tp = pair0; tp < num_pairs && ok; tp += pair_step) {
+       const int slots = pair_len(P, tp, tiles_per_map);
+       for (int slot = 0; slot < slots && ok; ++slot) {
+        const TileRef tr = tile_ref2(P, tp, (int)rank, slot, tiles_per_map);
+        const int n = tr.n, r = tr.r;
+        const int y0 = (r / P.tiles_x) * TILE_H, x0 = (r % P.tiles_x) * TILE_W;
+        const uint32_t image = (uint32_t)(P.drop.image0 + n / reps);
+        const uint32_t sample = (uint32_t)((n / P.drop.passes) % P.drop.samples);
+        const uint32_t c1w = pod_dropout_c1(P.drop.level, P.mask_in_layer, P.drop.tower, P.drop.pass0 + n % P.drop.passes);
+        for (int cb = 0; cb < kb_per_tap && ok; ++cb) {
+          if (tr.ok) {
+            __syncwarp();                                 // the previous K-block's table is no longer read
+            // 720 table entries per warp = 22.5 per lane; four independent Philox chains in flight per lane (a single
+            // warp cannot hide the ten dependent rounds of one call otherwise)
+            constexpr int TAB = 5 * (TILE_W + 2) * 8;
+#pragma unroll 1
+            for (int it0 = lane; it0 < TAB; it0 += 128) {
+              uint32_t ctr[4];
+              bool in[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int it = it0 + 32 * u;
+                const int g = it & 7, q = (it >> 3) % (TILE_W + 2), rr = (it >> 3) / (TILE_W + 2);
+                const int y = y0 - 1 + row0 + rr, x = x0 - 1 + q;
+                in[u] = it < TAB && y >= 0 && y < P.H && x >= 0 && x < P.W;
+                ctr[u] = (uint32_t)((((long long)y * P.W + x) * P.Cin + cb * 64 + g * 8) >> 3);
+              }
+              uint4 w[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) w[u] = philox4x32_10(ctr[u], c1w, sample, image, P.key);
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (it0 + 32 * u < TAB) tab[it0 + 32 * u] = in[u] ? (uint8_t)pod_keep8(w[u], P.drop_thr) : (uint8_t)0xFF;
+            }
+            __syncwarp();
+          }
+          for (int dx = 0; dx < 3 && ok; ++dx) {
+            int okw = 1;
+            if (lane == 0) okw = mbar_wait(&afull_bar[as], aphase, 17) ? 1 : 0;
+            if (!__shfl_sync(0xffffffffu, okw, 0)) { ok = false; break; }
+            if (tr.ok) {
+              uint8_t* sa = smem + (size_t)as * HALO_A_STAGE;
+              // 640 16-byte chunks (8 channels) per warp and stage = 20 per lane: AND the hi and the lo chunk with the
+              // element mask (16-byte read-modify-write, no branches; four chunks in flight per lane)
+#pragma unroll 1
+              for (int it0 = lane; it0 < 5 * TILE_W * 8; it0 += 128) {
+                uint4 vh[4], vl[4];
+                uint32_t kb[4];
+                uint4* ph[4];
+                uint4* pl[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int it = it0 + 32 * u;                     // 640 = 5 x 128: every lane has exactly five rounds
+                  const int g = it & 7, q = (it >> 3) % TILE_W, rr = (it >> 3) / TILE_W;
+                  kb[u] = tab[(rr * (TILE_W + 2) + q + dx) * 8 + g];
+                  const int pix = (row0 + rr) * TILE_W + q;
+                  // SWIZZLE_128B: 16-byte chunk g of pixel row `pix` lives at chunk g ^ (pix % 8)
+                  ph[u] = reinterpret_cast<uint4*>(sa + pix * 128 + ((g ^ (pix & 7)) << 4));
+                  pl[u] = reinterpret_cast<uint4*>(sa + HALO_A_HALF + pix * 128 + ((g ^ (pix & 7)) << 4));
+                  vh[u] = *ph[u];
+                  vl[u] = *pl[u];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const uint32_t k = kb[u];
+                  const uint32_t m0 = ((k & 1u) ? 0x0000FFFFu : 0u) | ((k & 2u) ? 0xFFFF0000u : 0u);
+                  const uint32_t m1 = ((k & 4u) ? 0x0000FFFFu : 0u) | ((k & 8u) ? 0xFFFF0000u : 0u);
+                  const uint32_t m2 = ((k & 16u) ? 0x0000FFFFu : 0u) | ((k & 32u) ? 0xFFFF0000u : 0u);
+                  const uint32_t m3 = ((k & 64u) ? 0x0000FFFFu : 0u) | ((k & 128u) ? 0xFFFF0000u : 0u);
+                  if (k != 0xFFu) {
+                    *ph[u] = make_uint4(vh[u].x & m0, vh[u].y & m1, vh[u].z & m2, vh[u].w & m3);
+                    *pl[u] = make_uint4(vl[u].x & m0, vl[u].y & m1, vl[u].z & m2, vl[u].w & m3);
+                  }
+                }
+              }
+              fence_proxy_async_smem();                   // generic-proxy stores -> visible to tcgen05.mma's operand reads
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_release(mapa_cluster(smem_u32(&amask_bar[as]), 0));
+            if (++as == CH::A_STAGES) { as = 0; aphase ^= 1u; }
+          }
+        }
+       }
+      }
+    }
   } else if (warp == 1 && rank == 0) {
     // ================================ MMA issuer (leader CTA; whole warp, one elected lane issues) ====
     const uint32_t leader = elect_one_sync();
@@ -1006,7 +1150,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
           for (int j = 0; j < kb_per_chunk; ++j) {
-            if (dy == 0 && !mbar_wait_all(&afull_bar[as], aphase, 16)) { ok = false; break; }
+            if (dy == 0 && !mbar_wait_all(MASKA ? &amask_bar[as] : &afull_bar[as], aphase, 16)) { ok = false; break; }
+            if (MASKA && dy == 0) fence_acq_rel_cluster();           // the peer's mask warps released at cluster scope
             if (!mbar_wait_all(&full_bar[stage], phase, 13)) { ok = false; break; }
             tcgen05_fence_after();
             const uint32_t sa_hi = smem_base + as * HALO_A_STAGE + dy * HALO_ROW_BYTES;
@@ -1204,10 +1349,10 @@ static int launch(const Params& P, cudaStream_t st) {
   return 0;
 }
 
-template <int BK, int MODE, bool HALO>
+template <int BK, int MODE, bool HALO, bool MASKA = false>
 static int launch2(const Params& P, cudaStream_t st) {
-  constexpr int SMEM = HALO ? CfgH2::SMEM_BYTES : Cfg2<BK>::SMEM_BYTES;
-  auto kern = k_conv3x3_tc2<BK, MODE, HALO>;
+  constexpr int SMEM = MASKA ? CfgH2M::SMEM_BYTES : (HALO ? CfgH2::SMEM_BYTES : Cfg2<BK>::SMEM_BYTES);
+  auto kern = k_conv3x3_tc2<BK, MODE, HALO, MASKA>;
   static bool configured = false;
   if (!configured) {
     POD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -1771,6 +1916,25 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
     P.q1_num_pairs = (int)((units + 1) / 2);
   }
   cudaStream_t st = (cudaStream_t)stream;
+  P.drop_scale_only = 0;
+  if (a->drop_scale_only && a->mode == POD_OUT_HIDDEN && a->drop.p > 0.0) {
+    // producer of c1 for a mask_in consumer: every element kept, multiplied by 1/(1-p)
+    P.drop_thr = 0;
+    P.drop_scale_only = 1;
+  }
+  if (a->mask_in) {
+    // first masked tower layer: the dropout mask of its INPUT is applied in shared memory (template MASKA)
+    POD_REQUIRE(halo && tc::g_tc_pair && a->mode == POD_OUT_HIDDEN && a->Cout_pad == 256 && a->Cin == 256 && a->drop.p > 0.0 &&
+                    a->q1_acc == nullptr, "pod_conv3x3_tc: mask_in needs the row-halo CTA-pair hidden-layer kernel with dropout");
+    const int reps = P.drop.samples * P.drop.passes;
+    POD_REQUIRE(a->NB % reps == 0, "pod_conv3x3_tc: mask_in maps must be images x samples x passes");
+    const int images = a->NB / reps;
+    if ((rc = encode_act(&P.tm_a_hi, a->in_hi, a->Cin, a->W, a->H, images, (long long)a->H * a->W * a->Cin, 64, HALO_ROWS))) return rc;
+    if ((rc = encode_act(&P.tm_a_lo, a->in_lo, a->Cin, a->W, a->H, images, (long long)a->H * a->W * a->Cin, 64, HALO_ROWS))) return rc;
+    P.mask_in = 1;
+    P.mask_in_layer = a->mask_in_layer;
+    return launch2<64, POD_OUT_HIDDEN, true, true>(P, st);
+  }
   if (halo) {
     return a->mode == POD_OUT_HIDDEN ? dispatch_bn<64, POD_OUT_HIDDEN, true>(P, st) : dispatch_bn<64, POD_OUT_RAW, true>(P, st);
   }

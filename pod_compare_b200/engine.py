@@ -152,6 +152,11 @@ class HeadEngine:
         self.device = torch.device(device)
         self._buf = {}
         self.profile_layers = False       # bench --profile-layers: tag tower launches by layer in ops.PROFILE
+        # MC-dropout: apply the first dropout inside the layer-1 convolution (pod_conv_args.mask_in) instead of writing the
+        # N x passes masked copies of the hoisted first layer with pod_mask_expand_split.  Bit-identical results, but
+        # measured SLOWER (two mask warps cannot draw 8192 Philox decisions per K-block in the 1536 cycles its MMAs take:
+        # layer 1 goes 164 -> 391 ms for the 16.9 ms of replication saved), so off by default.
+        self.mask_in_kernel = False
 
     # ------------------------------------------------------------------ buffers (reused across calls)
     def _get(self, name, numel, dtype):
@@ -252,6 +257,7 @@ class HeadEngine:
               "act": [(self._get("a%d_hi" % i, nmaps * max_hw * 256, torch.float16),
                        self._get("a%d_lo" % i, nmaps * max_hw * 256, torch.float16)) for i in range(2)],
               "c1": self._get("c1", B * max_hw * 256, torch.float32),
+              "c1_pair": (self._get("c1_hi", B * max_hw * 256, torch.float16), self._get("c1_lo", B * max_hw * 256, torch.float16)),
               "groups": (n_mc + Q1_GROUP - 1) // Q1_GROUP, "q1_acc": None, "q1_mean": None}
         if fuse:
             if in_epilogue:
@@ -278,21 +284,31 @@ class HeadEngine:
         tw = w.towers[tower]
         has_var = pc.cls_var if tower == TOWER_CLS else pc.bbox_cov
         t_passes = 2 if has_var else 1
-        # layer 0: conv + ReLU once per image, then N x passes masked copies (Q2 hoist)
+        # layer 0: conv + ReLU once per image (Q2 hoist: it does not depend on the dropout masks)
         p0 = tw[0]
-        ops.conv3x3_tc(fhi, flo, 1.0, B, H, W, 256, p0.w_hi, p0.w_lo, p0.w_scale, p0.bias, 256, 256,
-                       POD_OUT_RAW, True, out_f32=c1, out_map_stride=HW * 256, out_pixel_stride=256,
-                       in_scale_dev=fscale)
         d0 = ops.make_dropout(pc.dropout_rate, seed, image0, n_mc, t_passes, 0, tower, 0, lvl)
         # maps of one image: sample-major, pass-minor; the unread ones (skip_unread) are its tail
         grp = n_mc * t_passes
         live = grp
         if skip_unread and n_mc > 1:
             live = (n_mc - 1) * t_passes + (0 if tower == TOWER_CLS else 1)
-        ops.mask_expand_split(c1[: B * HW * 256].view(B, HW, 256), d0, 1.0, act[0][0], act[0][1], live_reps=live,
-                              scale_dev=fscale)
-        cur = 0
         NB = B * n_mc * t_passes
+        # in-kernel input masking needs a plain (non-accumulating) layer 1 on the CTA-pair row-halo kernel
+        mask_in = self.mask_in_kernel and len(tw) >= 2 and not (in_epilogue and len(tw) == 2)
+        if mask_in:
+            # c1 * 1/(1-p) as ONE split-pair map per image; layer 1 applies every (sample, pass) mask to its staged tiles
+            c1p = st["c1_pair"]
+            ops.conv3x3_tc(fhi, flo, 1.0, B, H, W, 256, p0.w_hi, p0.w_lo, p0.w_scale, p0.bias, 256, 256,
+                           POD_OUT_HIDDEN, True, out_hi=c1p[0], out_lo=c1p[1], out_scale=1.0, drop=d0, drop_scale_only=True,
+                           in_scale_dev=fscale, out_scale_dev=fscale, tag="conv1")
+        else:
+            ops.conv3x3_tc(fhi, flo, 1.0, B, H, W, 256, p0.w_hi, p0.w_lo, p0.w_scale, p0.bias, 256, 256,
+                           POD_OUT_RAW, True, out_f32=c1, out_map_stride=HW * 256, out_pixel_stride=256,
+                           in_scale_dev=fscale)
+            # the N x passes masked, rescaled, split copies of the first layer
+            ops.mask_expand_split(c1[: B * HW * 256].view(B, HW, 256), d0, 1.0, act[0][0], act[0][1], live_reps=live,
+                                  scale_dev=fscale)
+        cur = 0
         # passes of this tower whose last layer is only ever averaged over the samples (fused Q1 mean)
         acc_mask = 0
         if fuse:
@@ -309,6 +325,14 @@ class HeadEngine:
                                q1={"acc": q1_acc, "samples": n_mc, "passes": t_passes, "live": q1_live[:t_passes],
                                    "mask": acc_mask, "group": Q1_GROUP})
                 ops.q1_finish(q1_acc, B * n_acc, groups, HW * 256, n_mc, fscale, q1_mean[0], q1_mean[1])
+            elif mask_in and layer == 1:
+                ops.conv3x3_tc(c1p[0], c1p[1], 1.0, NB, H, W, 256, tw[layer].w_hi, tw[layer].w_lo, tw[layer].w_scale,
+                               tw[layer].bias, 256, 256, POD_OUT_HIDDEN, True, out_hi=act[cur ^ 1][0], out_lo=act[cur ^ 1][1],
+                               out_scale=1.0, drop=d, map_group=grp, map_live=live, in_scale_dev=fscale, out_scale_dev=fscale,
+                               mask_in=0, tag="tower256" if not self.profile_layers else "tower256_L1")
+                if acc_mask and layer == len(tw) - 1:
+                    ops.q1_mean_act(act[cur ^ 1][0], act[cur ^ 1][1], B, n_mc, t_passes, acc_mask, q1_live[:t_passes],
+                                    HW * 256, fscale, q1_mean[0], q1_mean[1])
             else:
                 self._conv_hidden(act[cur], NB, H, W, tw[layer], act[cur ^ 1], d, fscale, map_group=grp, map_live=live,
                                   tag="tower256" if not self.profile_layers else "tower256_L%d" % layer)

@@ -174,7 +174,7 @@ def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias,
                out_hi=None, out_lo=None, out_scale=1.0, out_f32=None, out_map_stride=0, out_pixel_stride=0,
                drop=None, in_map_stride=None, in_offset=0, out_offset=0, out2_f32=None, out2_offset=0, split_col=0,
                out2_map_stride=0, out2_pixel_stride=0, map_group=0, map_live=0, in_scale_dev=None, out_scale_dev=None,
-               q1=None, tag=None):
+               q1=None, tag=None, mask_in=None, drop_scale_only=False):
     """Raw-pointer launch of the tcgen05 convolution. `in_offset`/`out_offset` are ELEMENT offsets
     into in_hi/in_lo and out_f32.  in_scale_dev: 1-element fp32 CUDA tensor replacing in_scale."""
     lib = _cabi.require_device()
@@ -200,6 +200,9 @@ def conv3x3_tc(in_hi, in_lo, in_scale, NB, H, W, Cin, w_hi, w_lo, w_scale, bias,
     a.map_group, a.map_live = int(map_group), int(map_live)
     a.in_scale_dev = in_scale_dev.data_ptr() if in_scale_dev is not None else None
     a.out_scale_dev = out_scale_dev.data_ptr() if out_scale_dev is not None else None
+    if mask_in is not None:
+        a.mask_in, a.mask_in_layer = 1, int(mask_in)       # in-kernel dropout of the input (include/podb200.h)
+    a.drop_scale_only = int(bool(drop_scale_only))
     if q1 is not None:
         # Q1 sample accumulation of the last tower layer (include/podb200.h, pod_conv_args.q1_acc)
         a.q1_acc = q1["acc"].data_ptr()

@@ -691,6 +691,11 @@ def test_ensemble_members_read_their_own_feature_maps():
     assert torch.allclose(raw_own["logits"][0, 1].cpu(), ref_logits, rtol=1e-4, atol=2e-5)
     with pytest.raises(Exception):
         pred.infer_from_features(feats[:2], hw, out_hw, image0=img, seed=seed)    # 2 sets for 3 members
+    # the reference-style call with per-member features in the input dict: features[e][l]
+    pred.rng_seed = seed
+    inst = pred([{"image_hw": hw, "height": out_hw[0], "width": out_hw[1], "image_id": img, "features": feats}])
+    assert len(inst) == len(own[0]) and torch.equal(inst.scores, own[0].scores)
+    assert torch.equal(inst.pred_boxes_covariance, own[0].pred_boxes_covariance)
 
 
 # ------------------------------------------------------------------------------------------ the BASELINE.json configs
@@ -971,3 +976,41 @@ def test_fused_sample_mean_with_more_samples_than_one_group():
         want = ops.sample_mean_q1(raw_u[k])
         for got in (raw_f[k][:, 0], raw_s[k][:, 0]):
             assert float((got - want).abs().max()) <= 2e-6 * float(want.abs().max()), k
+
+
+# ------------------------------------------------------------------------------------------ in-kernel input dropout
+@pytest.mark.parametrize("name", ["mcdrop_pre_n4", "droponly_pre_n3", "mcdrop_single"])
+def test_in_kernel_input_masking_is_bit_identical_to_mask_replication(name):
+    """pod_conv_args.mask_in: the first masked tower layer applies the dropout mask of every (sample, pass) to its staged
+    input tile in shared memory (warps 2-3 of the CTA-pair kernel) instead of reading N x passes masked copies written by
+    pod_mask_expand_split.  Same operands into the same MMAs: every raw output must be bit-identical, for ragged tiles,
+    odd tile counts, batches, the unread-pass selection and single-run dropout."""
+    opts, mode, n_mc, seeds, hw, out_hw, seed, img = C.CASES[name]
+    cfg, pp, sds, feats = _oracle_case(name)
+    pred = build_predictor(cfg)
+    pred.load_weight_sets(sds[0])
+    eng = pred._engine
+    shapes = [(13, 21), (8, 16), (5, 7), (2, 3), (1, 1)]
+    dev = [torch.randn((3, 256, h, w), generator=torch.Generator().manual_seed(40 + i)).cuda().contiguous() for i, (h, w) in enumerate(shapes)]
+    out = {}
+    for inside in (False, True):
+        eng.mask_in_kernel = inside
+        for skip in ((False, True) if n_mc > 1 else (False,)):
+            raw, _ = eng.head_mc(dev, max(n_mc, 1), seed, img, skip_unread=skip, fuse_q1=False)
+            torch.cuda.synchronize()
+            assert ops.status() == 0
+            out[(inside, skip)] = {k: (v.clone() if v is not None else None) for k, v in raw.items()}
+    for skip in ((False, True) if n_mc > 1 else (False,)):
+        a, b = out[(False, skip)], out[(True, skip)]
+        live = max(n_mc, 1) - (1 if skip else 0)
+        assert torch.equal(a["deltas"], b["deltas"])
+        for k in ("logits", "logvar", "regvar"):
+            if a[k] is not None:
+                assert torch.equal(a[k][:, :live], b[k][:, :live]), (k, skip)
+    # and through the product path (fused sample mean, in-kernel masking still switched on) at the fixture geometry,
+    # against the oracle
+    res, _, cand, det = pred.infer_from_features(feats, hw, out_hw, image0=img, seed=seed, return_candidates=True)
+    torch.set_num_threads(8)
+    ref_final, ref_cand, ref_det = O.predict(feats, [O.unpack_head(sds[0], pp)], pp, mode, hw, out_hw=out_hw, n_mc=n_mc, seed=seed,
+                                             image=img, return_candidates=True, keep_diag=True, mc_single=C.is_mc_single(name))
+    _compare_path(res[0], cand, det, ref_final, ref_cand, ref_det, pp, False)
