@@ -281,6 +281,7 @@ def main():
                          "oracle of backbone_tc.py, for comparison)")
     ap.add_argument("--profile-layers", action="store_true", help="report tower time per layer in ms_per_step_by_kernel")
     ap.add_argument("--halo", type=int, default=-1, help="row-halo activation staging: bit 0 = pixels-as-M kernels, bit 1 = weights-as-A kernel (default 3)")
+    ap.add_argument("--tile-width", type=int, default=0, help="pixel-tile width of the CTA-pair tower kernel: 16, 32, 0 = per map shape (default)")
     ap.add_argument("--chunk-taps", type=int, default=0, help="taps per accumulation chunk (1, 3, 9)")
     ap.add_argument("--chunk-kblocks", type=int, default=0, help="K-blocks per accumulation chunk (overrides --chunk-taps)")
     ap.add_argument("--trunc-comp", type=float, default=-1.0, help="truncation compensation, ulps per MMA accumulation")
@@ -305,6 +306,8 @@ def main():
         ops.set_conv_pair(args.pair)
     if args.halo >= 0:
         ops.set_conv_halo(args.halo)
+    if args.tile_width:
+        ops.set_conv_tile_width(args.tile_width)
     if args.chunk_taps:
         ops.set_conv_chunk_taps(args.chunk_taps)
     if args.chunk_kblocks:

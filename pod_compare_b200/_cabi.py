@@ -15,7 +15,7 @@ EXPORTS = [
     "pod_conv3x3_tc_set_wait_limit", "pod_conv3x3_tc_debug_fault", "pod_conv3x3_tc_debug_clock",
     "pod_philox_dropout_mask", "pod_philox_logit_normals", "pod_philox_box_normals",
     "pod_nchw_to_nhwc_split", "pod_nchw_to_nhwc_f32", "pod_pack_conv_weight", "pod_pack_conv_weight_f32",
-    "pod_mask_expand_split", "pod_conv3x3_tc", "pod_conv3x3_tc_set_kblock", "pod_conv3x3_tc_set_chunk_taps", "pod_conv3x3_tc_set_chunk_kblocks", "pod_conv3x3_tc_set_pair", "pod_conv3x3_tc_set_halo", "pod_conv3x3_tc_set_wt", "pod_conv3x3_tc_set_trunc_comp", "pod_conv3x3_tc_status",
+    "pod_mask_expand_split", "pod_conv3x3_tc", "pod_conv3x3_tc_set_kblock", "pod_conv3x3_tc_set_chunk_taps", "pod_conv3x3_tc_set_chunk_kblocks", "pod_conv3x3_tc_set_pair", "pod_conv3x3_tc_set_tile_width", "pod_conv3x3_tc_set_halo", "pod_conv3x3_tc_set_wt", "pod_conv3x3_tc_set_trunc_comp", "pod_conv3x3_tc_status",
     "pod_conv3x3_simt", "pod_sample_mean_q1", "pod_scores", "pod_topk_levels", "pod_decode_cov", "pod_nms_fuse",
     "pod_cluster_merge", "pod_wire_records", "pod_q1_finish", "pod_q1_mean_act",
     "pod_conv_tc_general", "pod_pack_conv_weight_k", "pod_stem_conv7_pool", "pod_upsample2_add", "pod_split_f32",
@@ -133,6 +133,7 @@ def load_library():
     lib.pod_conv3x3_tc_set_chunk_taps.argtypes = [C.c_int]
     lib.pod_conv3x3_tc_set_chunk_kblocks.argtypes = [C.c_int]
     lib.pod_conv3x3_tc_set_pair.argtypes = [C.c_int]
+    lib.pod_conv3x3_tc_set_tile_width.argtypes = [C.c_int]
     lib.pod_conv3x3_tc_set_halo.argtypes = [C.c_int]
     lib.pod_conv3x3_tc_set_wt.argtypes = [C.c_int]
     lib.pod_conv3x3_tc_set_trunc_comp.argtypes = [C.c_float]

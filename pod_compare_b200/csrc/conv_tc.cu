@@ -351,14 +351,25 @@ struct CfgH {
   static_assert(B_HALF % 1024 == 0, "weight tile must keep 1024-B (swizzle atom) alignment");
 };
 
-// CTA pairs (N = 256 across the pair): every CTA stages 128 weight rows per tap
-struct CfgH2 {
+// CTA pairs (N = 256 across the pair): every CTA stages 128 weight rows per tap.  TW = tile width in pixels (the tile is
+// TW x 128/TW): 16 x 8 is the default; 32 x 4 covers maps whose height is badly divisible by 8 with fewer tiles (160 x 90:
+// 115 instead of 120 -- every tile is 27 648 MMA-cycles at 1 kW) at the price of a taller halo share (6 staged rows per 4
+// instead of 10 per 8).  A staged row of 32 pixels is 4096 B, so the dy advance stays a whole number of swizzle atoms.
+// A_ST = activation stages (3 for the in-kernel input masking, see MASKA).
+template <int TW, int A_ST>
+struct CfgH2G {
+  static_assert(TW == 16 || TW == 32, "tile width");
+  static constexpr int TH = 128 / TW;
+  static constexpr int ROW_BYTES = TW * 128;
+  static constexpr int A_HALF = (TH + 2) * ROW_BYTES;       // one of (hi, lo): 20 KB (16 x 8) or 24 KB (32 x 4)
+  static constexpr int A_STAGE = 2 * A_HALF;
   static constexpr int B_HALF = 128 * 128;
   static constexpr int B_STAGE = 2 * B_HALF;
-  static constexpr int A_STAGES = 2;
-  static constexpr int B_STAGES = (HALO_SMEM_BUDGET - 1024 - A_STAGES * HALO_A_STAGE) / B_STAGE;
-  static constexpr int SMEM_BYTES = 1024 + A_STAGES * HALO_A_STAGE + B_STAGES * B_STAGE;
+  static constexpr int A_STAGES = A_ST;
+  static constexpr int B_STAGES = (HALO_SMEM_BUDGET - 1024 - A_STAGES * A_STAGE) / B_STAGE;
+  static constexpr int SMEM_BYTES = 1024 + A_STAGES * A_STAGE + B_STAGES * B_STAGE;
   static_assert(B_STAGES >= 3, "weight ring too shallow");
+  static_assert(ROW_BYTES % 1024 == 0 && A_HALF % 1024 == 0, "tap advance must keep the swizzle phase");
 };
 
 // bias / ReLU / Philox dropout / store of one pixel row: NG groups of 16 accumulator columns from `sum`
@@ -877,15 +888,6 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint32_t leader) 
 }
 
 // MASKA: a third activation stage hides the extra hop (TMA -> mask warps -> MMA) of the in-kernel input masking
-struct CfgH2M {
-  static constexpr int B_HALF = 128 * 128;
-  static constexpr int B_STAGE = 2 * B_HALF;
-  static constexpr int A_STAGES = 3;
-  static constexpr int B_STAGES = (HALO_SMEM_BUDGET - 1024 - A_STAGES * HALO_A_STAGE) / B_STAGE;
-  static constexpr int SMEM_BYTES = 1024 + A_STAGES * HALO_A_STAGE + B_STAGES * B_STAGE;
-  static_assert(B_STAGES >= 3, "weight ring too shallow");
-};
-
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int BK>
@@ -901,10 +903,12 @@ struct Cfg2 {
   static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 };
 
-template <int BK, int MODE, bool HALO, bool MASKA = false>
+template <int BK, int MODE, bool HALO, bool MASKA = false, int TW = TILE_W>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_conv3x3_tc2(const __grid_constant__ Params P) {
   using C = Cfg2<BK>;
-  using CH = typename std::conditional<MASKA, CfgH2M, CfgH2>::type;   // each CTA stages 128 of the 256 weight rows
+  using CH = CfgH2G<TW, MASKA ? 3 : 2>;                 // each CTA stages 128 of the 256 weight rows
+  constexpr int TH = 128 / TW;
+  static_assert(TW == TILE_W || (HALO && !MASKA), "the 32 x 4 tile exists for the plain row-halo kernel");
   static_assert(!HALO || BK == 64, "row-halo staging needs 128-byte operand rows");
   static_assert(!MASKA || (HALO && MODE == POD_OUT_HIDDEN), "input masking exists for the row-halo hidden-layer kernel");
   constexpr int STAGES = HALO ? CH::B_STAGES : C::STAGES;   // HALO: full/empty_bar track the WEIGHT ring
@@ -987,31 +991,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
       // a CTA without work in this slot (odd tail, shorter unit) loads map index NB: entirely out of bounds -> zero fill
       const TileRef tr = tile_ref2(P, tp, (int)rank, slot, tiles_per_map);
       const int n = tr.n, r = tr.r;
-      const int y0 = (r / P.tiles_x) * TILE_H, x0 = (r % P.tiles_x) * TILE_W;
+      const int y0 = (r / P.tiles_x) * TH, x0 = (r % P.tiles_x) * TW;
       if constexpr (HALO) {
         for (int cb = 0; cb < kb_per_tap && ok; ++cb) {
           for (int dx = 0; dx < 3 && ok; ++dx) {
             if (!mbar_wait(&aempty_bar[as], aphase ^ 1u, 15)) { ok = false; break; }
-            uint8_t* sa = smem + (size_t)as * HALO_A_STAGE;
+            uint8_t* sa = smem + (size_t)as * CH::A_STAGE;
             if constexpr (MASKA) {
               // the tile of c1 (one map per image) lands under THIS CTA's barrier; its mask warps take it from there
               const int reps = P.drop.samples * P.drop.passes;
               const int img = tr.ok ? n / reps : P.NB / reps;           // no work: map index past the end -> zero fill
-              mbar_arrive_expect_tx(&afull_bar[as], (uint32_t)HALO_A_STAGE);
+              mbar_arrive_expect_tx(&afull_bar[as], (uint32_t)CH::A_STAGE);
               tma_load_4d(&P.tm_a_hi, &afull_bar[as], sa, cb * 64, x0 + dx - 1, y0 - 1, img);
-              tma_load_4d(&P.tm_a_lo, &afull_bar[as], sa + HALO_A_HALF, cb * 64, x0 + dx - 1, y0 - 1, img);
+              tma_load_4d(&P.tm_a_lo, &afull_bar[as], sa + CH::A_HALF, cb * 64, x0 + dx - 1, y0 - 1, img);
             } else {
-              if (rank == 0) mbar_arrive_expect_tx(&afull_bar[as], 2u * (uint32_t)HALO_A_STAGE);
+              if (rank == 0) mbar_arrive_expect_tx(&afull_bar[as], 2u * (uint32_t)CH::A_STAGE);
               const uint32_t fa = mapa_cluster(smem_u32(&afull_bar[as]), 0);    // the leader's barriers
               tma2_load_4d(&P.tm_a_hi, fa, sa, cb * 64, x0 + dx - 1, y0 - 1, n);
-              tma2_load_4d(&P.tm_a_lo, fa, sa + HALO_A_HALF, cb * 64, x0 + dx - 1, y0 - 1, n);
+              tma2_load_4d(&P.tm_a_lo, fa, sa + CH::A_HALF, cb * 64, x0 + dx - 1, y0 - 1, n);
             }
             if (++as == CH::A_STAGES) { as = 0; aphase ^= 1u; }
             for (int dy = 0; dy < 3; ++dy) {
               if (!mbar_wait(&empty_bar[stage], phase ^ 1u, 11)) { ok = false; break; }
               if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)CH::B_STAGE);
               const uint32_t fb = mapa_cluster(smem_u32(&full_bar[stage]), 0);
-              uint8_t* sb = smem + CH::A_STAGES * HALO_A_STAGE + (size_t)stage * CH::B_STAGE;
+              uint8_t* sb = smem + CH::A_STAGES * CH::A_STAGE + (size_t)stage * CH::B_STAGE;
               const int kcol = (dy * 3 + dx) * P.Cin + cb * 64;
               tma2_load_2d(&P.tm_b_hi, fb, sb, kcol, (int)rank * 128);
               tma2_load_2d(&P.tm_b_lo, fb, sb + CH::B_HALF, kcol, (int)rank * 128);
@@ -1054,7 +1058,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
        for (int slot = 0; slot < slots && ok; ++slot) {
         const TileRef tr = tile_ref2(P, tp, (int)rank, slot, tiles_per_map);
         const int n = tr.n, r = tr.r;
-        const int y0 = (r / P.tiles_x) * TILE_H, x0 = (r % P.tiles_x) * TILE_W;
+        const int y0 = (r / P.tiles_x) * TH, x0 = (r % P.tiles_x) * TW;
         const uint32_t image = (uint32_t)(P.drop.image0 + n / reps);
         const uint32_t sample = (uint32_t)((n / P.drop.passes) % P.drop.samples);
         const uint32_t c1w = pod_dropout_c1(P.drop.level, P.mask_in_layer, P.drop.tower, P.drop.pass0 + n % P.drop.passes);
@@ -1090,7 +1094,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
             if (lane == 0) okw = mbar_wait(&afull_bar[as], aphase, 17) ? 1 : 0;
             if (!__shfl_sync(0xffffffffu, okw, 0)) { ok = false; break; }
             if (tr.ok) {
-              uint8_t* sa = smem + (size_t)as * HALO_A_STAGE;
+              uint8_t* sa = smem + (size_t)as * CH::A_STAGE;
               // 640 16-byte chunks (8 channels) per warp and stage = 20 per lane: AND the hi and the lo chunk with the
               // element mask (16-byte read-modify-write, no branches; four chunks in flight per lane)
 #pragma unroll 1
@@ -1107,7 +1111,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
                   const int pix = (row0 + rr) * TILE_W + q;
                   // SWIZZLE_128B: 16-byte chunk g of pixel row `pix` lives at chunk g ^ (pix % 8)
                   ph[u] = reinterpret_cast<uint4*>(sa + pix * 128 + ((g ^ (pix & 7)) << 4));
-                  pl[u] = reinterpret_cast<uint4*>(sa + HALO_A_HALF + pix * 128 + ((g ^ (pix & 7)) << 4));
+                  pl[u] = reinterpret_cast<uint4*>(sa + CH::A_HALF + pix * 128 + ((g ^ (pix & 7)) << 4));
                   vh[u] = *ph[u];
                   vl[u] = *pl[u];
                 }
@@ -1154,9 +1158,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
             if (MASKA && dy == 0) fence_acq_rel_cluster();           // the peer's mask warps released at cluster scope
             if (!mbar_wait_all(&full_bar[stage], phase, 13)) { ok = false; break; }
             tcgen05_fence_after();
-            const uint32_t sa_hi = smem_base + as * HALO_A_STAGE + dy * HALO_ROW_BYTES;
-            const uint32_t sa_lo = sa_hi + HALO_A_HALF;
-            const uint32_t sb_hi = smem_base + CH::A_STAGES * HALO_A_STAGE + stage * CH::B_STAGE;
+            const uint32_t sa_hi = smem_base + as * CH::A_STAGE + dy * CH::ROW_BYTES;
+            const uint32_t sa_lo = sa_hi + CH::A_HALF;
+            const uint32_t sb_hi = smem_base + CH::A_STAGES * CH::A_STAGE + stage * CH::B_STAGE;
             const uint32_t sb_lo = sb_hi + CH::B_HALF;
             const uint64_t ah0 = make_smem_desc<128>(sa_hi), al0 = make_smem_desc<128>(sa_lo);
             const uint64_t bh0 = make_smem_desc<128>(sb_hi), bl0 = make_smem_desc<128>(sb_lo);
@@ -1232,7 +1236,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) k_co
       const TileRef tr = tile_ref2(P, tp, (int)rank, slot, tiles_per_map);
       const bool tile_ok = tr.ok != 0;
       const int n = tile_ok ? tr.n : 0, r = tr.r;
-      const int py = (r / P.tiles_x) * TILE_H + m / TILE_W, px = (r % P.tiles_x) * TILE_W + m % TILE_W;
+      const int py = (r / P.tiles_x) * TH + m / TW, px = (r % P.tiles_x) * TW + m % TW;
       const bool valid = tile_ok && py < P.H && px < P.W;
       const int pixel = py * P.W + px;
       float sum[COLS];
@@ -1349,10 +1353,10 @@ static int launch(const Params& P, cudaStream_t st) {
   return 0;
 }
 
-template <int BK, int MODE, bool HALO, bool MASKA = false>
+template <int BK, int MODE, bool HALO, bool MASKA = false, int TW = TILE_W>
 static int launch2(const Params& P, cudaStream_t st) {
-  constexpr int SMEM = MASKA ? CfgH2M::SMEM_BYTES : (HALO ? CfgH2::SMEM_BYTES : Cfg2<BK>::SMEM_BYTES);
-  auto kern = k_conv3x3_tc2<BK, MODE, HALO, MASKA>;
+  constexpr int SMEM = HALO ? CfgH2G<TW, MASKA ? 3 : 2>::SMEM_BYTES : Cfg2<BK>::SMEM_BYTES;
+  auto kern = k_conv3x3_tc2<BK, MODE, HALO, MASKA, TW>;
   static bool configured = false;
   if (!configured) {
     POD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -1653,9 +1657,26 @@ static int launch_wt(const Params& P, cudaStream_t st) {
 
 static int g_tc_pair = 1;   // 1: 256-channel convs run on CTA pairs (cta_group::2); 0: single-CTA kernel
 
+static int g_tc_tile_w = 0;   // CTA-pair row-halo kernel: 0 = pick per map shape, 16 / 32 = force the tile width
+
+// Tile width of the CTA-pair row-halo kernel for an H x W map: 32 x 4 only where it saves more tiles than its taller
+// halo costs (6 staged rows per 4 output rows instead of 10 per 8: +20 % activation bytes into the SM, worth about
+// 1 % of clock on the power-bound tower) -- in practice P3 of a 1280 x 720 frame (160 x 90: 115 tiles instead of 120).
+static int pick_tile_width(int H, int W) {
+  if (g_tc_tile_w == 16 || g_tc_tile_w == 32) return g_tc_tile_w;
+  const long long t16 = (long long)((W + 15) / 16) * ((H + 7) / 8);
+  const long long t32 = (long long)((W + 31) / 32) * ((H + 3) / 4);
+  return t32 * 1000 < t16 * 980 ? 32 : 16;
+}
+
 template <int BK, int MODE, bool HALO>
-static int dispatch_bn(const Params& P, cudaStream_t st) {
-  if (P.Cout_pad == 256 && g_tc_pair) return launch2<BK, MODE, HALO>(P, st);
+static int dispatch_bn(const Params& P, cudaStream_t st, int tw = TILE_W) {
+  if (P.Cout_pad == 256 && g_tc_pair) {
+    if constexpr (HALO) {
+      if (tw == 32) return launch2<BK, MODE, HALO, false, 32>(P, st);
+    }
+    return launch2<BK, MODE, HALO>(P, st);
+  }
   switch (P.Cout_pad) {
     case 256: return launch<256, BK, MODE, HALO>(P, st);
     case 128: return launch<128, BK, MODE, HALO>(P, st);
@@ -1749,6 +1770,12 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_halo(in
   return 0;
 }
 
+extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_tile_width(int tw) {
+  POD_REQUIRE(tw == 0 || tw == 16 || tw == 32, "pod_conv3x3_tc_set_tile_width: 0 (per map shape), 16 or 32");
+  tc::g_tc_tile_w = tw;
+  return 0;
+}
+
 extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc_set_pair(int on) {
   tc::g_tc_pair = on ? 1 : 0;
   return 0;
@@ -1820,10 +1847,13 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
     return wt_halo ? launch_wt<true>(P, (cudaStream_t)stream) : launch_wt<false>(P, (cudaStream_t)stream);
   }
   const bool halo = (g_tc_halo & 1) && BK == 64;
-  const int box_rows = halo ? HALO_ROWS : TILE_H;
+  // tile geometry: 16 x 8 pixels everywhere except where the CTA-pair row-halo kernel does better with 32 x 4
+  const int tw = (halo && a->Cout_pad == 256 && tc::g_tc_pair && !a->mask_in) ? pick_tile_width(a->H, a->W) : TILE_W;
+  const int th = 128 / tw;
+  const int box_rows = halo ? th + 2 : th;
   int rc;
-  if ((rc = encode_act(&P.tm_a_hi, a->in_hi, a->Cin, a->W, a->H, a->NB, a->in_map_stride, BK, box_rows))) return rc;
-  if ((rc = encode_act(&P.tm_a_lo, a->in_lo, a->Cin, a->W, a->H, a->NB, a->in_map_stride, BK, box_rows))) return rc;
+  if ((rc = encode_act(&P.tm_a_hi, a->in_hi, a->Cin, a->W, a->H, a->NB, a->in_map_stride, BK, box_rows, tw))) return rc;
+  if ((rc = encode_act(&P.tm_a_lo, a->in_lo, a->Cin, a->W, a->H, a->NB, a->in_map_stride, BK, box_rows, tw))) return rc;
   // CTA pairs stage half of the 256 weight rows each
   const int b_box_rows = (a->Cout_pad == 256 && tc::g_tc_pair) ? 128 : a->Cout_pad;
   if ((rc = encode_wt(&P.tm_b_hi, a->w_hi, 9 * a->Cin, a->Cout_pad, BK, b_box_rows))) return rc;
@@ -1831,8 +1861,8 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
   P.NB = a->NB; P.H = a->H; P.W = a->W; P.Cin = a->Cin;
   P.taps = 9; P.ksz = 3; P.stride = 1; P.pad = 1; P.w_row0 = 0;
   P.out_ch_stride = a->Cout_pad; P.out_ch_off = 0;
-  P.tiles_x = (a->W + TILE_W - 1) / TILE_W;
-  P.tiles_y = (a->H + TILE_H - 1) / TILE_H;
+  P.tiles_x = (a->W + tw - 1) / tw;
+  P.tiles_y = (a->H + th - 1) / th;
   P.map_group = P.map_live = 1;
   long long logical_maps = a->NB;
   if (a->map_group > 0) {
@@ -1936,7 +1966,7 @@ extern "C" __attribute__((visibility("default"))) int pod_conv3x3_tc(const pod_c
     return launch2<64, POD_OUT_HIDDEN, true, true>(P, st);
   }
   if (halo) {
-    return a->mode == POD_OUT_HIDDEN ? dispatch_bn<64, POD_OUT_HIDDEN, true>(P, st) : dispatch_bn<64, POD_OUT_RAW, true>(P, st);
+    return a->mode == POD_OUT_HIDDEN ? dispatch_bn<64, POD_OUT_HIDDEN, true>(P, st, tw) : dispatch_bn<64, POD_OUT_RAW, true>(P, st, tw);
   }
   if (BK == 64) {
     return a->mode == POD_OUT_HIDDEN ? dispatch_bn<64, POD_OUT_HIDDEN, false>(P, st)

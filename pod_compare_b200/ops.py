@@ -287,6 +287,11 @@ def set_conv_pair(on):
     check(_cabi.load_library().pod_conv3x3_tc_set_pair(int(bool(on))), "pod_conv3x3_tc_set_pair")
 
 
+def set_conv_tile_width(tw):
+    """0 = per map shape (default), 16 or 32: pixel-tile width of the CTA-pair row-halo kernel (bit-identical results)."""
+    check(_cabi.load_library().pod_conv3x3_tc_set_tile_width(int(tw)), "pod_conv3x3_tc_set_tile_width")
+
+
 def set_conv_trunc_comp(ulps_per_mma):
     check(_cabi.load_library().pod_conv3x3_tc_set_trunc_comp(float(ulps_per_mma)), "pod_conv3x3_tc_set_trunc_comp")
 

@@ -270,6 +270,43 @@ def _hidden_dropout_and_strided_input():
     assert G.rel_err(got2, ref2) < 1e-5
 
 
+TILE_WIDTH_SHAPES = [  # (NB, H, W): 256 -> 256 channels on the CTA-pair row-halo kernel
+    (1, 4, 32),        # exactly one 32 x 4 tile (odd tile count: the pair's idle CTA)
+    (2, 90, 160),      # P3 of a 1280 x 720 frame: 115 tiles of 32 x 4 against 120 of 16 x 8 (the shape the choice exists for)
+    (3, 13, 21),       # ragged in both directions for both geometries
+    (2, 5, 37),        # one row / five columns past a tile
+    (5, 1, 1),         # single pixel
+    (1, 23, 40),       # P5
+]
+
+
+@pytest.mark.parametrize("shape", TILE_WIDTH_SHAPES)
+def test_tc_conv_tile_width_32_is_bit_identical_to_16(shape):
+    """pod_conv3x3_tc_set_tile_width: the CTA-pair row-halo kernel covers a map with 16 x 8 or 32 x 4 pixel tiles.  Every
+    output pixel sees the same K order of the same MMAs either way, so raw outputs, hidden activations (hi / lo pairs)
+    and the in-epilogue dropout must be bit-identical; the default (0) picks per map shape."""
+    NB, H, W = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((NB, 256, H, W), generator=g) * 1.5
+    w = torch.randn((256, 256, 3, 3), generator=g) * (2.0 / 2304) ** 0.5
+    b = torch.randn((256,), generator=g) * 0.05
+    d = ops.make_dropout(0.1, 77, 3, 1, 1, 2, 1, 2, 0)
+    out = {}
+    try:
+        for tw in (16, 32, 0):
+            ops.set_conv_tile_width(tw)
+            raw = G.tc_conv_raw(x, w, b, False)
+            hid = G.tc_conv_hidden(x, w, b, d)
+            assert ops.status() == 0
+            out[tw] = (raw, hid)
+    finally:
+        ops.set_conv_tile_width(0)
+    assert G.rel_err(out[16][0], G.conv_ref64(x, w, b, False)) < 1e-5
+    for tw in (32, 0):
+        assert torch.equal(out[tw][0], out[16][0]), tw
+        assert torch.equal(out[tw][1], out[16][1]), tw
+
+
 # ------------------------------------------------------------------------------------------ scores / top-k
 def _level_off(level_hw, A=9):
     off = [0]
