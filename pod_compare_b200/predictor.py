@@ -371,6 +371,12 @@ class ProbabilisticPredictor:
         level_hw = [tuple(f.shape[-2:]) for f in (feats[0] if per_member else feats)]
         anchors = self._anchors(level_hw)
         if mode == 'ensembles':
+            if self.mc_dropout_enabled:
+                # The reference does not compose the two: with NUM_RUNS > 1 its pre-NMS branch discards the members'
+                # outputs and runs MC-dropout on the un-loaded base model (probabilistic_inference.py:196-205), and its
+                # post-NMS branch replicates every eval()-mode member NUM_RUNS times.  None of its configs enables both.
+                raise _cabi.PodError("INFERENCE_MODE 'ensembles' with MC_DROPOUT.ENABLE is not supported (the reference "
+                                     "does not combine them either: see predictor.py)")
             if len(self.weight_sets) != len(pi.ENSEMBLES.RANDOM_SEED_NUMS):
                 raise _cabi.PodError("ensembles mode needs one weight set per RANDOM_SEED_NUMS entry")
             raw, level_off = eng.head_eval(feats, skip_unread=self.skip_unread_outputs and not post_nms,

@@ -696,6 +696,15 @@ def test_ensemble_members_read_their_own_feature_maps():
     inst = pred([{"image_hw": hw, "height": out_hw[0], "width": out_hw[1], "image_id": img, "features": feats}])
     assert len(inst) == len(own[0]) and torch.equal(inst.scores, own[0].scores)
     assert torch.equal(inst.pred_boxes_covariance, own[0].pred_boxes_covariance)
+    # 'ensembles' together with MC_DROPOUT.ENABLE is not a combination the reference composes (its pre-NMS branch would
+    # silently run MC-dropout on the un-loaded base model instead): an explicit error here, never a quiet guess
+    cfg2 = cfg.clone()
+    cfg2.defrost()
+    cfg2.PROBABILISTIC_INFERENCE.MC_DROPOUT.ENABLE = True
+    pred2 = build_predictor(cfg2)
+    pred2.load_weight_sets(sds)
+    with pytest.raises(PodError, match="ensembles"):
+        pred2.infer_from_features(feats, hw, out_hw, image0=img, seed=seed)
 
 
 # ------------------------------------------------------------------------------------------ the BASELINE.json configs

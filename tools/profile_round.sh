@@ -14,6 +14,7 @@ mkdir -p gpurun_out
 G=gpurun_out/${TAG}
 timeout 2400 python -m pytest tests -m gpu -q 2>&1 | tail -40 > ${G}_pytest_gpu.txt
 tail -3 ${G}_pytest_gpu.txt
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > ${G}_smoke.txt 2>&1; tail -1 ${G}_smoke.txt
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > ${G}_clocks.csv &
 SMI=$!
 timeout 900 python bench.py > ${G}_bench_n1.json 2> ${G}_bench_n1.err
