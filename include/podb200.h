@@ -208,7 +208,7 @@ int pod_conv3x3_tc_set_halo(int mode);
 /* 256-output-channel convolutions on CTA pairs (tcgen05 cta_group::2, default on) or on single CTAs. */
 int pod_conv3x3_tc_set_pair(int on);
 /* Pixel-tile width of the CTA-pair row-halo kernel: 16 (16 x 8 tiles), 32 (32 x 4 tiles) or 0 = chosen per map shape
- * (default: 32 x 4 where it covers the map with >= 2 % fewer tiles, e.g. 160 x 90).  Every output pixel sees the same
+ * (default: 32 x 4 where it covers the map with >= 2 % fewer tiles, e.g. 160 x 92).  Every output pixel sees the same
  * MMAs in the same order either way: results are bit-identical.  Process-wide tuning / test knob. */
 int pod_conv3x3_tc_set_tile_width(int tw);
 /* Device-side error word of the tcgen05 kernels only (see pod_status).  Host pointer out. */

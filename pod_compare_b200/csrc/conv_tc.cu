@@ -352,7 +352,7 @@ struct CfgH {
 };
 
 // CTA pairs (N = 256 across the pair): every CTA stages 128 weight rows per tap.  TW = tile width in pixels (the tile is
-// TW x 128/TW): 16 x 8 is the default; 32 x 4 covers maps whose height is badly divisible by 8 with fewer tiles (160 x 90:
+// TW x 128/TW): 16 x 8 is the default; 32 x 4 covers maps whose height is badly divisible by 8 with fewer tiles (160 x 92:
 // 115 instead of 120 -- every tile is 27 648 MMA-cycles at 1 kW) at the price of a taller halo share (6 staged rows per 4
 // instead of 10 per 8).  A staged row of 32 pixels is 4096 B, so the dy advance stays a whole number of swizzle atoms.
 // A_ST = activation stages (3 for the in-kernel input masking, see MASKA).
@@ -1661,7 +1661,7 @@ static int g_tc_tile_w = 0;   // CTA-pair row-halo kernel: 0 = pick per map shap
 
 // Tile width of the CTA-pair row-halo kernel for an H x W map: 32 x 4 only where it saves more tiles than its taller
 // halo costs (6 staged rows per 4 output rows instead of 10 per 8: +20 % activation bytes into the SM, worth about
-// 1 % of clock on the power-bound tower) -- in practice P3 of a 1280 x 720 frame (160 x 90: 115 tiles instead of 120).
+// 1 % of clock on the power-bound tower) -- in practice P3 of a 1280 x 720 frame as detectron2 pads it (160 x 92: 115 tiles instead of 120).
 static int pick_tile_width(int H, int W) {
   if (g_tc_tile_w == 16 || g_tc_tile_w == 32) return g_tc_tile_w;
   const long long t16 = (long long)((W + 15) / 16) * ((H + 7) / 8);

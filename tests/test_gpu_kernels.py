@@ -272,7 +272,7 @@ def _hidden_dropout_and_strided_input():
 
 TILE_WIDTH_SHAPES = [  # (NB, H, W): 256 -> 256 channels on the CTA-pair row-halo kernel
     (1, 4, 32),        # exactly one 32 x 4 tile (odd tile count: the pair's idle CTA)
-    (2, 90, 160),      # P3 of a 1280 x 720 frame: 115 tiles of 32 x 4 against 120 of 16 x 8 (the shape the choice exists for)
+    (2, 92, 160),      # P3 of a 1280 x 720 frame: 115 tiles of 32 x 4 against 120 of 16 x 8 (the shape the choice exists for)
     (3, 13, 21),       # ragged in both directions for both geometries
     (2, 5, 37),        # one row / five columns past a tile
     (5, 1, 1),         # single pixel

@@ -19,6 +19,7 @@ pytestmark = pytest.mark.gpu
 from oracle import cases as C
 from oracle import podref as O
 from pod_compare_b200 import engine, ops, synthetic as S
+from pod_compare_b200._cabi import PodError
 from pod_compare_b200.predictor import build_predictor
 from tests import gpu_util as G
 
@@ -629,7 +630,6 @@ def test_large_feature_magnitudes_are_rescaled():
 def test_device_side_errors_reach_the_caller():
     """A bounded mbarrier wait that expires, or an activation outside the fp16 split range, must surface as PodError
     from the product call -- never as plausible-looking detections (the predictor polls pod_status once per call)."""
-    from pod_compare_b200._cabi import PodError
     name = "mcdrop_pre_n4"
     opts, mode, n_mc, seeds, hw, out_hw, seed, img = C.CASES[name]
     cfg, pp, sds, feats = _oracle_case(name)
