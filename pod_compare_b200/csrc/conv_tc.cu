@@ -3,14 +3,16 @@
 //   D[pixel, cout] = sum_{tap, cin} X[pixel + tap, cin] * Wt[cout, tap*Cin + cin]
 //
 // Three kernels share the TMA / mbarrier / tcgen05 plumbing of this file:
-//   k_conv3x3_tc2   256 -> 256 tower layers on CTA PAIRS (cta_group::2, M = 2 x 128 pixels, N = 256): 83 % of the step
+//   k_conv3x3_tc2   256 -> 256 tower layers on CTA PAIRS (cta_group::2, M = 2 x 128 pixels, N = 256): 90 % of the step;
+//                   pixel tiles of 16 x 8 or, per map shape, 32 x 4 (template TW); optional in-kernel input dropout (MASKA)
 //   k_conv3x3_wt    output convolutions of <= 64 channels, WEIGHTS as the A operand ([w_hi; w_lo] stacked along M = 128),
 //                   16 x 16 pixels as N = 256
 //   k_conv3x3_tc    everything else on a single CTA, pixels as M = 128, N = Cout_pad (hi|lo weights N-stacked for <= 128)
 //
 // * pixel operand: channels-last activation tiles fetched by TMA from a 4-D tensor map (C, W, H, maps); the zero
 //   padding is TMA's out-of-bounds fill.  Row-halo staging (default): one box two rows taller than the tile per column
-//   shift serves the three row-shifted taps through shared-memory descriptor offsets of whole 2048-byte pixel rows.
+//   shift serves the three row-shifted taps through shared-memory descriptor offsets of whole 2048-byte (16-pixel) or
+//   4096-byte (32-pixel) rows.
 // * weight operand: packed rows [Cout_pad][9*Cin] (hi rows, then lo rows, one buffer) fetched by TMA (2-D map).
 // * fp32 fidelity on fp16 tensor cores: both operands arrive as (hi, lo) fp16 pairs; hi*hi', hi*lo' and lo*hi' are
 //   accumulated in fp32 TMEM.  The K loop is cut into chunks (default 12 K-blocks of 64 channels) summed in alternating
@@ -20,7 +22,8 @@
 //   straight-line UTCHMMA) + TMEM allocator, warps 4-11 = epilogue (tcgen05.ld -> chunk sums -> bias / ReLU / Philox
 //   dropout -> fp16 split or fp32 store); setmaxnreg moves registers from warpgroup 0 to the epilogue warpgroups.
 // * persistent: grid = min(#tiles, #SMs), static round-robin over (live map, tile_y, tile_x); every mbarrier wait is
-//   bounded and reports through pod_conv3x3_tc_status instead of hanging the device.
+//   bounded and reports through pod_status / pod_conv3x3_tc_status instead of hanging the device; activations that leave
+//   the fp16 split range are reported the same way.
 //
 // Replaces nn.Conv2d(+ReLU+Dropout) of the reference head,
 // /root/reference/src/probabilistic_modeling/probabilistic_retinanet.py:401-441,458-484,517-523.
