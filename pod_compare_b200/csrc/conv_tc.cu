@@ -1662,9 +1662,10 @@ static int g_tc_pair = 1;   // 1: 256-channel convs run on CTA pairs (cta_group:
 
 static int g_tc_tile_w = 0;   // CTA-pair row-halo kernel: 0 = pick per map shape, 16 / 32 = force the tile width
 
-// Tile width of the CTA-pair row-halo kernel for an H x W map: 32 x 4 only where it saves more tiles than its taller
-// halo costs (6 staged rows per 4 output rows instead of 10 per 8: +20 % activation bytes into the SM, worth about
-// 1 % of clock on the power-bound tower) -- in practice P3 of a 1280 x 720 frame as detectron2 pads it (160 x 92: 115 tiles instead of 120).
+// Tile width of the CTA-pair row-halo kernel for an H x W map: 32 x 4 only where it covers the map with at least 2 % fewer
+// tiles -- about 60 % of the saved MMAs show up as time (measured), so small savings are not worth leaving
+// the reference geometry.  In practice: P3 of a 1280 x 720 frame as detectron2 pads it (160 x 92: 115 tiles instead of
+// 120) and P6 (20 x 12: 3 instead of 4).  An 8 x 16 tile (smallest halo share) was built and measured too: no gain.
 static int pick_tile_width(int H, int W) {
   if (g_tc_tile_w == 16 || g_tc_tile_w == 32) return g_tc_tile_w;
   const long long t16 = (long long)((W + 15) / 16) * ((H + 7) / 8);

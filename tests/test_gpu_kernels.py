@@ -272,6 +272,7 @@ def _hidden_dropout_and_strided_input():
 
 TILE_WIDTH_SHAPES = [  # (NB, H, W): 256 -> 256 channels on the CTA-pair row-halo kernel
     (1, 4, 32),        # exactly one 32 x 4 tile (odd tile count: the pair's idle CTA)
+    (2, 17, 9),        # narrower than either tile, one row past two 16 x 8 tiles
     (2, 92, 160),      # P3 of a 1280 x 720 frame: 115 tiles of 32 x 4 against 120 of 16 x 8 (the shape the choice exists for)
     (3, 13, 21),       # ragged in both directions for both geometries
     (2, 5, 37),        # one row / five columns past a tile
@@ -281,7 +282,7 @@ TILE_WIDTH_SHAPES = [  # (NB, H, W): 256 -> 256 channels on the CTA-pair row-hal
 
 
 @pytest.mark.parametrize("shape", TILE_WIDTH_SHAPES)
-def test_tc_conv_tile_width_32_is_bit_identical_to_16(shape):
+def test_tc_conv_tile_widths_are_bit_identical(shape):
     """pod_conv3x3_tc_set_tile_width: the CTA-pair row-halo kernel covers a map with 16 x 8 or 32 x 4 pixel tiles.  Every
     output pixel sees the same K order of the same MMAs either way, so raw outputs, hidden activations (hi / lo pairs)
     and the in-epilogue dropout must be bit-identical; the default (0) picks per map shape."""
