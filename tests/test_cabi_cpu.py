@@ -99,6 +99,40 @@ def test_reference_config_yaml_surface():
         assert c.is_frozen()
 
 
+def test_yaml_eval_tag_is_arithmetic_only(tmp_path):
+    """The reference's YAML carries `!!python/object/apply:eval` for the anchor sizes (Base-RetinaNet: a nested list
+    comprehension).  The loader evaluates that construct by walking a whitelisted AST -- arithmetic on numbers and
+    comprehension variables only -- so a config file shipped next to a checkpoint cannot run code: the classic
+    escapes from eval() with emptied builtins must be rejected, not executed."""
+    import yaml
+    from pod_compare_b200.config import _safe_arith_eval, load_yaml_with_base
+    got = _safe_arith_eval("[[x, x * 2**(1.0/3), x * 2**(2.0/3)] for x in [32, 64, 128, 256, 512]]")
+    assert len(got) == 5 and got[0][0] == 32 and abs(got[4][2] - 512 * 2 ** (2.0 / 3)) < 1e-9
+    assert _safe_arith_eval("[-(1 + 2) * 3, 7 // 2, 2 ** 10]") == [-9, 3, 1024]
+    for bad in ("().__class__.__base__.__subclasses__()",          # attribute walk to every loaded class
+                "__import__('os').system('true')",                  # call
+                "[x for x in range(3)]",                            # call as the iterable
+                "open('/etc/passwd')",
+                "(lambda: 1)()",
+                "[x for x in [1, 2] if x]",                         # filters are not part of the construct
+                "y + 1",                                            # free name
+                "[1, 2][0]",                                        # subscript
+                "'a' * 3",                                          # non-numeric constant
+                "2 ** 4096"):                                       # resource exhaustion
+        with pytest.raises((yaml.YAMLError, SyntaxError)):
+            _safe_arith_eval(bad)
+    # through the loader, as the tag appears in the reference's files
+    f = tmp_path / "c.yaml"
+    f.write_text("MODEL:\n  ANCHOR_GENERATOR:\n    SIZES: !!python/object/apply:eval [\"[[x, 2 * x] for x in [8, 16]]\"]\n")
+    assert load_yaml_with_base(str(f))["MODEL"]["ANCHOR_GENERATOR"]["SIZES"] == [[8, 16], [16, 32]]
+    f.write_text("X: !!python/object/apply:eval [\"__import__('os').getcwd()\"]\n")
+    with pytest.raises(yaml.YAMLError):
+        load_yaml_with_base(str(f))
+    f.write_text("X: !!python/object/apply:os.getcwd []\n")          # any other python tag stays unknown to the loader
+    with pytest.raises(yaml.YAMLError):
+        load_yaml_with_base(str(f))
+
+
 def test_backbone_shapes_and_keys_cpu():
     """The upstream ResNet-50-FPN restatement (library torch ops): detectron2 key coverage and the
     P3..P7 geometry (detectron2 pads to the res5 stride 32: 100x190 -> 128x192; P6 / P7 are stride-2 3x3 convolutions)."""
