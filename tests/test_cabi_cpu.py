@@ -99,6 +99,17 @@ def test_reference_config_yaml_surface():
         assert c.is_frozen()
 
 
+def test_build_predictor_rejects_other_meta_architectures_like_the_reference():
+    """probabilistic_inference.py:20-33: build_predictor raises ValueError('Invalid meta-architecture ...') for anything
+    but ProbabilisticRetinaNet -- before any device is touched, so the check also holds on a CPU-only host."""
+    from pod_compare_b200.config import get_cfg
+    from pod_compare_b200.predictor import build_predictor
+    cfg = get_cfg()
+    cfg.MODEL.META_ARCHITECTURE = "GeneralizedRCNN"
+    with pytest.raises(ValueError, match="Invalid meta-architecture GeneralizedRCNN"):
+        build_predictor(cfg)
+
+
 def test_yaml_eval_tag_is_arithmetic_only(tmp_path):
     """The reference's YAML carries `!!python/object/apply:eval` for the anchor sizes (Base-RetinaNet: a nested list
     comprehension).  The loader evaluates that construct by walking a whitelisted AST -- arithmetic on numbers and
